@@ -1,0 +1,310 @@
+// assembly.cu -- the value pass: fused Ke/Fe + MatSetValues(ADD) + Dirichlet lifting + VecSetValues(ADD).
+//
+// Replaces the element loop of the *parallelimpl1 drivers (tetrapoissonparallelimpl1.F:828-884,
+// tetraelasticityparallelimpl1.F:901-968) and PETSc's MatSetValues/VecSetValues behind it.
+//
+// Design (row gather, no atomics): one thread owns one matrix row.  It walks the row's incident
+// elements in ascending element id, recomputes the element geometry, and adds the row's slice of
+// Klocal (read transposed, as PETSc reads the column-major Fortran block) into the row's CSR segment,
+// which lives in shared memory for the whole CTA (a CTA owns R consecutive rows = one contiguous CSR
+// segment, loaded and stored with coalesced accesses).  Per matrix entry the contributions are thus
+// summed in exactly the order of the reference's sequential np=1 run, so the result is deterministic and,
+// because the TU is built with -fmad=false, bit-identical to the no-FMA CPU evaluation.
+#include "elements.cuh"
+#include "internal.cuh"
+
+namespace pfem {
+
+struct AsmArgs {
+    int nloc, row_lo, row_hi, rec_ints;
+    const int *erec;
+    const double *xyz;
+    const double *applied;
+    const int *rowptr, *col;
+    double *val, *rhs;
+    const int *rinc_ptr, *rinc;
+    const double *elemData, *timeData;
+    int *neg_count;
+    int load_val, load_rhs;
+    int max_seg_nnz;     // smem carve-up
+};
+
+template <int NPE, int NDIM>
+__device__ __forceinline__ void load_coords(const double *__restrict__ xyz, const int nodes[NPE], double x[NPE],
+                                            double y[NPE], double z[NPE])
+{
+#pragma unroll
+    for (int i = 0; i < NPE; i++) {
+        if (NDIM == 3) {
+            const double2 *p = reinterpret_cast<const double2 *>(xyz + (size_t)nodes[i] * 4);
+            const double2 a = __ldg(p), b = __ldg(p + 1);
+            x[i] = a.x; y[i] = a.y; z[i] = b.x;
+        } else {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(xyz + (size_t)nodes[i] * 2));
+            x[i] = a.x; y[i] = a.y; z[i] = 0.0;
+        }
+    }
+}
+
+template <int KIND, int R>
+__global__ void __launch_bounds__(R) assemble_kernel(const AsmArgs a)
+{
+    using T = ElemTraits<KIND>;
+    constexpr int NPE = T::NPE, NDOF = T::NDOF, NDIM = T::NDIM, NSIZE = NPE * NDOF;
+    constexpr int REC4 = (NPE + NSIZE + 3) / 4;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *acc = reinterpret_cast<double *>(smem_raw);
+    int *scol = reinterpret_cast<int *>(acc + a.max_seg_nnz);
+    int *sinc = scol + a.max_seg_nnz;
+
+    const int r0 = blockIdx.x * R;
+    const int rend = min(r0 + R, a.nloc);
+    const int nnz0 = a.rowptr[r0], nnz1 = a.rowptr[rend];
+    const int inc0 = a.rinc_ptr[r0], inc1 = a.rinc_ptr[rend];
+
+    // stage the CTA's CSR segment and incidence segment through shared memory (coalesced)
+    for (int k = threadIdx.x; k < nnz1 - nnz0; k += R) {
+        scol[k] = a.col[nnz0 + k];
+        acc[k] = a.load_val ? a.val[nnz0 + k] : 0.0;
+    }
+    for (int m = threadIdx.x; m < inc1 - inc0; m += R) sinc[m] = a.rinc[inc0 + m];
+    __syncthreads();
+
+    const int r = r0 + threadIdx.x;
+    if (r < rend) {
+        Params<KIND> prm;
+        prm.init(a.elemData, a.timeData);
+        const int seg = a.rowptr[r] - nnz0, len = a.rowptr[r + 1] - a.rowptr[r];
+        const int *rc = scol + seg;
+        double *racc = acc + seg;
+        double facc = a.load_rhs ? a.rhs[r] : 0.0;
+        const double du0[3] = {0.0, 0.0, 0.0};    // valC = 0 in the drivers (tetrapoissonparallelimpl1.F:824)
+        const int m1 = a.rinc_ptr[r + 1] - inc0;
+        for (int m = a.rinc_ptr[r] - inc0; m < m1; m++) {
+            const int code = sinc[m];
+            const int e = code / NSIZE, k = code - e * NSIZE;
+            int rec[REC4 * 4];
+            const int4 *rp = reinterpret_cast<const int4 *>(a.erec + (size_t)e * a.rec_ints);
+#pragma unroll
+            for (int q = 0; q < REC4; q++) {
+                const int4 v = __ldg(rp + q);
+                rec[4 * q] = v.x; rec[4 * q + 1] = v.y; rec[4 * q + 2] = v.z; rec[4 * q + 3] = v.w;
+            }
+            const int *nodes = rec, *dofs = rec + NPE;
+            double x[NPE], y[NPE], z[NPE];
+            load_coords<NPE, NDIM>(a.xyz, nodes, x, y, z);
+            ElemOp<KIND> op;
+            op.load_geom(x, y, z);
+            if (op.g.Jac < 0.0) {
+                // the reference STOPs here; report once per element (from its first owned local dof)
+                int first = 0;
+#pragma unroll
+                for (int q = NSIZE - 1; q >= 0; q--)
+                    if (dofs[q] >= a.row_lo && dofs[q] < a.row_hi) first = q;
+                if (first == k) atomicAdd(a.neg_count, 1);
+                continue;
+            }
+            op.set_dvol(prm);
+            // MatSetValues(ADD): entry (row k, col j) += Klocal(j, k)
+            op.col_setup(prm, k);
+#pragma unroll
+            for (int j = 0; j < NSIZE; j++) {
+                const int c = dofs[j];
+                if (c < 0) continue;
+                const double v = op.K(prm, j);
+                int lo = 0, hi = len;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (rc[mid] < c) lo = mid + 1; else hi = mid;
+                }
+                racc[lo] = racc[lo] + v;
+            }
+            // Flocal(k), then lifting in ascending Dirichlet local index: F_k -= Klocal(k, ii) * g_ii
+            double f = op.F(prm, k, du0);
+#pragma unroll
+            for (int ii = 0; ii < NSIZE; ii++) {
+                if (dofs[ii] != -1) continue;
+                const double gval = a.applied[(size_t)nodes[ii / NDOF] * NDOF + (ii % NDOF)];
+                op.col_setup(prm, ii);
+                f = f - op.K(prm, k) * gval;
+            }
+            facc = facc + f;      // VecSetValues(ADD)
+        }
+        a.rhs[r] = facc;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nnz1 - nnz0; k += R) a.val[nnz0 + k] = acc[k];
+}
+
+template <int KIND, int R>
+static int launch_assemble(pfem_solver *h, const AsmArgs &args)
+{
+    const int blocks = ceil_div(h->size_local, R);
+    if (blocks == 0) return PFEM_OK;
+    PFEM_CUDA(cudaFuncSetAttribute(assemble_kernel<KIND, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->asm_smem));
+    assemble_kernel<KIND, R><<<blocks, R, h->asm_smem, h->stream>>>(args);
+    h->launches++;
+    PFEM_CUDA(cudaGetLastError());
+    return PFEM_OK;
+}
+
+template <int KIND>
+static int dispatch_rows(pfem_solver *h, const AsmArgs &args)
+{
+    switch (h->asm_rows_per_cta) {
+    case 256: return launch_assemble<KIND, 256>(h, args);
+    case 128: return launch_assemble<KIND, 128>(h, args);
+    case 64: return launch_assemble<KIND, 64>(h, args);
+    case 32: return launch_assemble<KIND, 32>(h, args);
+    }
+    set_error("assembly: no CTA shape fits shared memory");
+    return PFEM_ERR_SIZE;
+}
+
+// Pick the rows-per-CTA so that the largest CTA segment (CSR values + columns + incidences) fits in smem.
+int plan_assembly(pfem_solver *h)
+{
+    const int nloc = h->size_local;
+    std::vector<int> rp((size_t)nloc + 1), ip((size_t)nloc + 1);
+    PFEM_CUDA(cudaMemcpy(rp.data(), h->rowptr.p, ((size_t)nloc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    PFEM_CUDA(cudaMemcpy(ip.data(), h->rinc_ptr.p, ((size_t)nloc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    int max_smem = 0;
+    PFEM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const int shapes[4] = {256, 128, 64, 32};
+    // prefer the largest shape that still lets two CTAs share an SM
+    for (int pass = 0; pass < 2; pass++) {
+        const size_t limit = pass == 0 ? (size_t)max_smem / 2 - 1024 : (size_t)max_smem;
+        for (int R : shapes) {
+            int mn = 0, mi = 0;
+            for (int r0 = 0; r0 < nloc; r0 += R) {
+                const int r1 = r0 + R < nloc ? r0 + R : nloc;
+                mn = std::max(mn, rp[r1] - rp[r0]);
+                mi = std::max(mi, ip[r1] - ip[r0]);
+            }
+            mn = (mn + 1) & ~1;   // keep the int arrays 8-byte aligned
+            const size_t bytes = (size_t)mn * 12 + (size_t)mi * 4 + 16;
+            if (bytes <= limit) {
+                h->asm_rows_per_cta = R;
+                h->asm_smem = bytes;
+                h->asm_max_seg = mn;
+                return PFEM_OK;
+            }
+        }
+    }
+    set_error("assembly: a 32-row CSR segment does not fit in %d bytes of shared memory", max_smem);
+    return PFEM_ERR_SIZE;
+}
+
+int assemble_values(pfem_solver *h, const double *elemData, const double *timeData, int *n_neg)
+{
+    if (h->asm_rows_per_cta == 0) PFEM_TRY(plan_assembly(h));
+    DevBuf<double> dED, dTD;
+    PFEM_TRY(dED.alloc(8));
+    PFEM_TRY(dTD.alloc(8));
+    double ed[8] = {0}, td[8] = {0};
+    const int ned = h->kind == PFEM_POISSON_TRIA ? 2 : h->kind == PFEM_POISSON_TETRA ? 3 : h->kind == PFEM_ELASTICITY_TRIA ? 5 : 6;
+    for (int i = 0; i < ned; i++) ed[i] = elemData[i];
+    td[1] = timeData[1];
+    cudaStream_t s = h->stream;
+    PFEM_CUDA(cudaMemcpyAsync(dED.p, ed, sizeof ed, cudaMemcpyHostToDevice, s));
+    PFEM_CUDA(cudaMemcpyAsync(dTD.p, td, sizeof td, cudaMemcpyHostToDevice, s));
+    PFEM_CUDA(cudaMemsetAsync(h->neg_count.p, 0, sizeof(int), s));
+    AsmArgs a;
+    a.nloc = h->size_local; a.row_lo = h->row_lo; a.row_hi = h->row_hi; a.rec_ints = h->rec_ints;
+    a.erec = h->erec.p; a.xyz = h->xyz.p; a.applied = h->applied.p;
+    a.rowptr = h->rowptr.p; a.col = h->col.p; a.val = h->val.p; a.rhs = h->rhs.p;
+    a.rinc_ptr = h->rinc_ptr.p; a.rinc = h->rinc.p;
+    a.elemData = dED.p; a.timeData = dTD.p; a.neg_count = h->neg_count.p;
+    a.load_val = h->values_zero ? 0 : 1; a.load_rhs = h->rhs_zero ? 0 : 1;
+    a.max_seg_nnz = h->asm_max_seg;
+    PFEM_CUDA(cudaEventRecord(h->ev0, s));
+    int st = PFEM_OK;
+    switch (h->kind) {
+    case PFEM_POISSON_TRIA: st = dispatch_rows<POISSON_TRIA>(h, a); break;
+    case PFEM_POISSON_TETRA: st = dispatch_rows<POISSON_TETRA>(h, a); break;
+    case PFEM_ELASTICITY_TRIA: st = dispatch_rows<ELASTICITY_TRIA>(h, a); break;
+    case PFEM_ELASTICITY_TETRA: st = dispatch_rows<ELASTICITY_TETRA>(h, a); break;
+    default: set_error("assemble: mesh kind not set"); return PFEM_ERR_STATE;
+    }
+    PFEM_TRY(st);
+    PFEM_CUDA(cudaEventRecord(h->ev1, s));
+    int neg = 0;
+    PFEM_CUDA(cudaMemcpyAsync(&neg, h->neg_count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    PFEM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->t_assemble = ms * 1e-3;
+    h->values_zero = false;
+    h->rhs_zero = false;
+    if (n_neg) *n_neg = neg;
+    if (neg) {
+        set_error("assembly: %d element(s) with negative Jacobian (the reference STOPs)", neg);
+        return PFEM_ERR_NEG_JACOBIAN;
+    }
+    return PFEM_OK;
+}
+
+// ---- slow-path adds: MatSetValues / VecSetValues / MatSetValue mirrors ----------------------------------------
+// One thread walks the block in PETSc's order (row by row, column by column).
+__global__ void add_entries_kernel(int n, const int *__restrict__ rows, const int *__restrict__ cols,
+                                   const double *__restrict__ vals, int transposed, const double *__restrict__ F,
+                                   int row_lo, int row_hi, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                   double *__restrict__ val, double *__restrict__ rhs)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int i = 0; i < n; i++) {
+        const int r = rows[i];
+        if (r < row_lo || r >= row_hi) continue;   // negative rows are dropped; other ranks' rows are theirs to add
+        const int lr = r - row_lo;
+        if (F) rhs[lr] = rhs[lr] + F[i];
+        if (!vals) continue;
+        for (int j = 0; j < n; j++) {
+            const int c = cols[j];
+            if (c < 0) continue;
+            int lo = rowptr[lr], hi = rowptr[lr + 1];
+            const int end = hi;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (col[mid] < c) lo = mid + 1; else hi = mid;
+            }
+            if (lo < end && col[lo] == c) {
+                const double v = transposed ? vals[j + n * i] : vals[i + n * j];
+                val[lo] = val[lo] + v;
+            }
+            // a location outside the pattern would be a new nonzero: the pattern pass fixed the structure
+        }
+    }
+}
+
+int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const double *vals, bool transposed,
+                const double *F)
+{
+    if (n <= 0 || !rows) { set_error("add: bad argument"); return PFEM_ERR_ARG; }
+    DevBuf<int> dr, dc;
+    DevBuf<double> dv, df;
+    cudaStream_t s = h->stream;
+    PFEM_TRY(dr.alloc(n));
+    PFEM_CUDA(cudaMemcpyAsync(dr.p, rows, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (vals) {
+        if (!cols) { set_error("add: cols missing"); return PFEM_ERR_ARG; }
+        PFEM_TRY(dc.alloc(n));
+        PFEM_TRY(dv.alloc((size_t)n * n));
+        PFEM_CUDA(cudaMemcpyAsync(dc.p, cols, n * sizeof(int), cudaMemcpyHostToDevice, s));
+        PFEM_CUDA(cudaMemcpyAsync(dv.p, vals, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    if (F) {
+        PFEM_TRY(df.alloc(n));
+        PFEM_CUDA(cudaMemcpyAsync(df.p, F, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    add_entries_kernel<<<1, 32, 0, s>>>(n, dr.p, vals ? dc.p : nullptr, vals ? dv.p : nullptr, transposed ? 1 : 0,
+                                        F ? df.p : nullptr, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, h->val.p, h->rhs.p);
+    h->launches++;
+    PFEM_CUDA(cudaGetLastError());
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    if (vals) h->values_zero = false;
+    if (F) h->rhs_zero = false;
+    return PFEM_OK;
+}
+
+}  // namespace pfem

@@ -1,0 +1,699 @@
+// cg.cu -- the KSP replacement: Jacobi-preconditioned CG with PETSc's KSPSolve_CG semantics.
+//
+// Replaces PetscSolver%solve -> KSPSolve (solverpetsc.F:431-490) and, inside PETSc, KSPSolve_CG,
+// PCApply_Jacobi, MatMult_MPIAIJ and VecDot/VecNorm/VecAXPY/VecAYPX.
+//
+//  * Matrix layout for the solve: the owned rows are split like PETSc's MPIAIJ into a diagonal block
+//    (columns owned by this rank) and an off-diagonal block (ghost columns).  The diagonal block is stored
+//    as SELL-32 (slices of 32 rows, column-major inside a slice): one thread per row, one warp per slice,
+//    every load of values/indices is a fully coalesced 256/128-byte warp access and there is no
+//    intra-row reduction.  Entries of a row are visited in ascending column order, like MatMult_SeqAIJ.
+//  * All CG scalars live on the device (CgState).  Each reduction is finalised by the last CTA to finish
+//    (fixed-order sum of the per-CTA partials => run-to-run deterministic); kernels early-out once
+//    `reason` is set, so the host only polls every few iterations and never stalls the pipeline.
+//  * Per iteration: direction (p = z + b p), SpMV fused with p.w, update (x, r, z, z.z, z.r fused).
+#include <cub/cub.cuh>
+
+#include "internal.cuh"
+
+namespace pfem {
+
+static constexpr int CG_THREADS = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// CTA-wide sum, result valid in thread 0.  Fixed tree => deterministic.
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (wid == 0) {
+        t = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+// Last-CTA-done: returns true (in every thread of the last CTA) once all CTAs have published partials.
+__device__ __forceinline__ bool last_block(unsigned int *ticket)
+{
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// fixed-order sum of n partials by one CTA (thread 0 gets the result)
+__device__ __forceinline__ double reduce_partials(const double *partials, int n, double *sh)
+{
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __ldcg(partials + i);
+    return block_sum(s, sh);
+}
+
+// ---- scalar steps of KSPSolve_CG (PETSc 3.6 cg.c), executed by one thread -------------------------------------
+
+__device__ int converged_default(CgState *st, int it, double rnorm)
+{
+    if (it == 0) { st->ttol = fmax(st->rtol * rnorm, st->abstol); st->rnorm0 = rnorm; }
+    if (isnan(rnorm) || isinf(rnorm)) return PFEM_DIVERGED_NANORINF;
+    if (rnorm <= st->ttol) return rnorm < st->abstol ? PFEM_CONVERGED_ATOL : PFEM_CONVERGED_RTOL;
+    if (rnorm >= st->dtol * st->rnorm0) return PFEM_DIVERGED_DTOL;
+    return 0;
+}
+
+__device__ void begin_iteration(CgState *st)
+{
+    st->its = st->iter + 1;
+    if (st->beta == 0.0) { st->reason = PFEM_CONVERGED_ATOL; return; }
+    if (st->iter > 0 && st->beta * st->betaold < 0.0) { st->reason = PFEM_DIVERGED_INDEFINITE_PC; return; }
+    st->b = st->iter == 0 ? 0.0 : st->beta / st->betaold;
+}
+
+__device__ void step_after_setup(CgState *st, double zz, double zr)
+{
+    st->dp = sqrt(zz);
+    st->its = 0; st->iter = 0; st->dpi = 0.0; st->betaold = 0.0;
+    st->reason = converged_default(st, 0, st->dp);
+    if (st->reason) return;
+    st->beta = zr;
+    begin_iteration(st);
+}
+
+__device__ void step_after_spmv(CgState *st, double pw)
+{
+    st->dpiold = st->dpi;
+    st->dpi = pw;
+    st->betaold = st->beta;
+    if (pw == 0.0 || (st->iter > 0 && pw * st->dpiold <= 0.0)) { st->reason = PFEM_DIVERGED_INDEFINITE_MAT; return; }
+    st->a = st->beta / pw;
+}
+
+__device__ void step_after_update(CgState *st, double zz, double zr)
+{
+    st->dp = sqrt(zz);
+    st->reason = converged_default(st, st->iter + 1, st->dp);
+    if (st->reason) return;
+    st->beta = zr;
+    st->iter++;
+    if (st->iter >= st->max_it) { st->reason = PFEM_DIVERGED_ITS; return; }
+    begin_iteration(st);
+}
+
+// single-thread kernels used when the sums had to cross ranks first (nranks > 1)
+__global__ void scalar_after_setup_kernel(CgState *st) { if (st->reason == 0 || st->iter < 0) step_after_setup(st, st->red[0], st->red[1]); }
+__global__ void scalar_after_spmv_kernel(CgState *st) { if (st->reason == 0) step_after_spmv(st, st->red[0]); }
+__global__ void scalar_after_update_kernel(CgState *st) { if (st->reason == 0) step_after_update(st, st->red[0], st->red[1]); }
+
+// ---- solver-structure construction (pattern time) -----------------------------------------------------------------
+
+__global__ void classify_rows_kernel(int nloc, int row_lo, int row_hi, const int *__restrict__ rowptr,
+                                     const int *__restrict__ col, int *__restrict__ ndiag, int *__restrict__ noff)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += gridDim.x * blockDim.x) {
+        int nd = 0, no = 0;
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const int c = col[k];
+            if (c >= row_lo && c < row_hi) nd++; else no++;
+        }
+        ndiag[r] = nd;
+        noff[r] = no;
+    }
+}
+
+// one warp per slice: padded slice size = 32 * max(ndiag)
+__global__ void slice_width_kernel(int nloc, int nslices, const int *__restrict__ ndiag, long long *__restrict__ slice_sz)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += warps) {
+        const int r = s * 32 + lane;
+        int w = r < nloc ? ndiag[r] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+        if (lane == 0) slice_sz[s] = (long long)w * 32;
+    }
+}
+
+__global__ void gather_offdiag_cols_kernel(int nloc, int row_lo, int row_hi, const int *__restrict__ rowptr,
+                                           const int *__restrict__ col, const int *__restrict__ off_ptr,
+                                           int *__restrict__ out)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += gridDim.x * blockDim.x) {
+        int o = off_ptr[r];
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const int c = col[k];
+            if (c < row_lo || c >= row_hi) out[o++] = c;
+        }
+    }
+}
+
+__global__ void fill_structures_kernel(int nloc, int nrows_padded, int row_lo, int row_hi, const int *__restrict__ rowptr,
+                                       const int *__restrict__ col, const long long *__restrict__ slice_off,
+                                       const int *__restrict__ off_ptr, const int *__restrict__ ghost, int n_ghost,
+                                       int *__restrict__ sell_col, int *__restrict__ bcol, int *__restrict__ csr2sell)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows_padded; r += gridDim.x * blockDim.x) {
+        const int s = r >> 5, lane = r & 31;
+        const long long base = slice_off[s] + lane;
+        const int width = (int)((slice_off[s + 1] - slice_off[s]) >> 5);
+        int kd = 0;
+        if (r < nloc) {
+            int ko = off_ptr[r];
+            for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+                const int c = col[k];
+                if (c >= row_lo && c < row_hi) {
+                    const long long d = base + (long long)kd * 32;
+                    sell_col[d] = c - row_lo;
+                    csr2sell[k] = (int)d;
+                    kd++;
+                } else {
+                    int lo = 0, hi = n_ghost;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (ghost[mid] < c) lo = mid + 1; else hi = mid;
+                    }
+                    bcol[ko] = lo;
+                    csr2sell[k] = -ko - 1;
+                    ko++;
+                }
+            }
+        }
+        // padding: value 0 times a valid local entry (the row itself, or row 0 past the end)
+        const int self = r < nloc ? r : 0;
+        for (; kd < width; kd++) sell_col[base + (long long)kd * 32] = self;
+    }
+}
+
+__global__ void boundary_rows_kernel(int nloc, const int *__restrict__ noff, const int *__restrict__ brow_rank,
+                                     const int *__restrict__ off_ptr, int *__restrict__ brow_ids, int *__restrict__ brow_ptr,
+                                     int n_brows, int nnz_off)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += gridDim.x * blockDim.x) {
+        if (noff[r] > 0) {
+            const int q = brow_rank[r];
+            brow_ids[q] = r;
+            brow_ptr[q] = off_ptr[r];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) brow_ptr[n_brows] = nnz_off;
+}
+
+__global__ void flag_kernel(int n, const int *__restrict__ v, int *__restrict__ f)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f[i] = v[i] > 0 ? 1 : 0;
+}
+
+template <typename T>
+static int exclusive_scan(pfem_solver *h, const T *in, T *out, int n)
+{
+    size_t bytes = 0;
+    PFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream));
+    DevBuf<char> tmp;
+    PFEM_TRY(tmp.alloc(bytes));
+    PFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, h->stream));
+    h->launches++;
+    return PFEM_OK;
+}
+
+int build_solver_structures(pfem_solver *h)
+{
+    cudaStream_t s = h->stream;
+    const int nloc = h->size_local, G = h->sm_count * 8;
+    const int nslices = (nloc + 31) / 32, nrows_padded = nslices * 32;
+    DevBuf<int> ndiag, noff, off_ptr, flags, brow_rank;
+    DevBuf<long long> slice_sz;
+    PFEM_TRY(ndiag.alloc((size_t)nloc + 1));
+    PFEM_TRY(noff.alloc((size_t)nloc + 1));
+    PFEM_TRY(off_ptr.alloc((size_t)nloc + 1));
+    PFEM_TRY(flags.alloc((size_t)nloc + 1));
+    PFEM_TRY(brow_rank.alloc((size_t)nloc + 1));
+    PFEM_TRY(slice_sz.alloc((size_t)nslices + 1));
+    PFEM_CUDA(cudaMemsetAsync(ndiag.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
+    PFEM_CUDA(cudaMemsetAsync(noff.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
+    PFEM_CUDA(cudaMemsetAsync(flags.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
+    PFEM_CUDA(cudaMemsetAsync(slice_sz.p, 0, ((size_t)nslices + 1) * sizeof(long long), s));
+    classify_rows_kernel<<<G, 256, 0, s>>>(nloc, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, ndiag.p, noff.p);
+    slice_width_kernel<<<G, 256, 0, s>>>(nloc, nslices, ndiag.p, slice_sz.p);
+    flag_kernel<<<G, 256, 0, s>>>(nloc, noff.p, flags.p);
+    h->launches += 3;
+    h->A.nrows = nloc; h->A.nslices = nslices;
+    PFEM_TRY(h->A.slice_off.alloc((size_t)nslices + 1));
+    PFEM_TRY(exclusive_scan<long long>(h, slice_sz.p, h->A.slice_off.p, nslices + 1));
+    PFEM_TRY(exclusive_scan<int>(h, noff.p, off_ptr.p, nloc + 1));
+    PFEM_TRY(exclusive_scan<int>(h, flags.p, brow_rank.p, nloc + 1));
+    long long nstored = 0;
+    int nnz_off = 0, n_brows = 0;
+    PFEM_CUDA(cudaMemcpyAsync(&nstored, h->A.slice_off.p + nslices, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaMemcpyAsync(&nnz_off, off_ptr.p + nloc, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaMemcpyAsync(&n_brows, brow_rank.p + nloc, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    if (nstored >= (1LL << 31)) { set_error("SELL storage (%lld entries) exceeds 2^31", nstored); return PFEM_ERR_SIZE; }
+    h->A.nstored = nstored; h->nnz_off = nnz_off; h->n_brows = n_brows;
+    PFEM_TRY(h->A.col.alloc((size_t)nstored));
+    PFEM_TRY(h->A.val.alloc((size_t)nstored));
+    PFEM_CUDA(cudaMemsetAsync(h->A.val.p, 0, (size_t)(nstored > 0 ? nstored : 1) * sizeof(double), s));
+    PFEM_TRY(h->csr2sell.alloc((size_t)h->nnz));
+    PFEM_TRY(h->bcol.alloc((size_t)nnz_off));
+    PFEM_TRY(h->bval.alloc((size_t)nnz_off));
+    PFEM_TRY(h->brow_ids.alloc((size_t)n_brows + 1));
+    PFEM_TRY(h->brow_ptr.alloc((size_t)n_brows + 1));
+    // ghost list = sorted unique off-diagonal global columns (PETSc's garray)
+    DevBuf<int> ghost;
+    h->ghost_cols.clear();
+    h->n_ghost = 0;
+    if (nnz_off > 0) {
+        DevBuf<int> oc, oc_sorted, nsel;
+        PFEM_TRY(oc.alloc((size_t)nnz_off));
+        PFEM_TRY(oc_sorted.alloc((size_t)nnz_off));
+        PFEM_TRY(ghost.alloc((size_t)nnz_off));
+        PFEM_TRY(nsel.alloc(1));
+        gather_offdiag_cols_kernel<<<G, 256, 0, s>>>(nloc, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, off_ptr.p, oc.p);
+        h->launches++;
+        size_t b1 = 0, b2 = 0;
+        PFEM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b1, oc.p, oc_sorted.p, nnz_off, 0, 32, s));
+        PFEM_CUDA(cub::DeviceSelect::Unique(nullptr, b2, oc_sorted.p, ghost.p, nsel.p, nnz_off, s));
+        DevBuf<char> tmp;
+        PFEM_TRY(tmp.alloc(b1 > b2 ? b1 : b2));
+        PFEM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, b1, oc.p, oc_sorted.p, nnz_off, 0, 32, s));
+        PFEM_CUDA(cub::DeviceSelect::Unique(tmp.p, b2, oc_sorted.p, ghost.p, nsel.p, nnz_off, s));
+        h->launches += 2;
+        int ng = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&ng, nsel.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        h->n_ghost = ng;
+        h->ghost_cols.resize(ng);
+        PFEM_CUDA(cudaMemcpy(h->ghost_cols.data(), ghost.p, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+        PFEM_TRY(ghost.alloc(1));
+    }
+    fill_structures_kernel<<<G, 256, 0, s>>>(nloc, nrows_padded, h->row_lo, h->row_hi, h->rowptr.p, h->col.p,
+                                             h->A.slice_off.p, off_ptr.p, ghost.p, h->n_ghost, h->A.col.p, h->bcol.p,
+                                             h->csr2sell.p);
+    boundary_rows_kernel<<<G, 256, 0, s>>>(nloc, noff.p, brow_rank.p, off_ptr.p, h->brow_ids.p, h->brow_ptr.p, n_brows, nnz_off);
+    h->launches += 2;
+    PFEM_CUDA(cudaGetLastError());
+    // vectors (padded to whole slices so the SpMV tail needs no guards on reads)
+    const size_t nv = (size_t)nrows_padded + 32;
+    PFEM_TRY(h->x.alloc(nv)); PFEM_TRY(h->r.alloc(nv)); PFEM_TRY(h->z.alloc(nv));
+    PFEM_TRY(h->p.alloc(nv)); PFEM_TRY(h->w.alloc(nv)); PFEM_TRY(h->dinv.alloc(nv));
+    PFEM_CUDA(cudaMemsetAsync(h->x.p, 0, nv * sizeof(double), s));
+    PFEM_CUDA(cudaMemsetAsync(h->p.p, 0, nv * sizeof(double), s));
+    PFEM_CUDA(cudaMemsetAsync(h->w.p, 0, nv * sizeof(double), s));
+    PFEM_TRY(h->ghost_buf.alloc((size_t)h->n_ghost + 1));
+    PFEM_TRY(h->partials.alloc((size_t)4 * h->sm_count * 16));
+    if (!h->cg.p) {
+        PFEM_TRY(h->cg.alloc(1));
+        PFEM_CUDA(cudaMemsetAsync(h->cg.p, 0, sizeof(CgState), s));
+    }
+    if (!h->cg_host) PFEM_CUDA(cudaMallocHost((void **)&h->cg_host, sizeof(CgState)));
+    // halo plan: ghosts are sorted by global id, hence grouped by owner rank in ascending order
+    const int P = h->nranks;
+    h->send_counts.assign(P, 0); h->recv_counts.assign(P, 0);
+    h->send_displs.assign(P + 1, 0); h->recv_displs.assign(P + 1, 0);
+    if (P > 1) {
+        std::vector<int> need_counts(P, 0);
+        int q = 0;
+        for (int g : h->ghost_cols) {
+            while (g >= h->row_starts[q + 1]) q++;
+            need_counts[q]++;
+        }
+        std::vector<int> asked, asked_counts;
+        PFEM_TRY(comm_alltoallv_int(h, h->ghost_cols, need_counts, asked, asked_counts));
+        h->recv_counts = need_counts;        // what I receive during a halo exchange = my ghosts
+        h->send_counts = asked_counts;       // what I send = rows the others asked for
+        for (int i = 0; i < P; i++) {
+            h->send_displs[i + 1] = h->send_displs[i] + h->send_counts[i];
+            h->recv_displs[i + 1] = h->recv_displs[i] + h->recv_counts[i];
+        }
+        std::vector<int> sidx(asked.size());
+        for (size_t i = 0; i < asked.size(); i++) {
+            sidx[i] = asked[i] - h->row_lo;
+            if (sidx[i] < 0 || sidx[i] >= nloc) { set_error("halo plan: rank asked for a row this rank does not own"); return PFEM_ERR_NUMBERING; }
+        }
+        PFEM_TRY(h->send_idx.alloc(sidx.size() + 1));
+        PFEM_TRY(h->send_buf.alloc(sidx.size() + 1));
+        if (!sidx.empty()) PFEM_CUDA(cudaMemcpy(h->send_idx.p, sidx.data(), sidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    return PFEM_OK;
+}
+
+// ---- solve-time kernels ----------------------------------------------------------------------------------------------
+
+// CSR values -> solver storage (SELL diagonal block / off-diagonal CSR)
+__global__ void values_to_solver_kernel(long long nnz, const double *__restrict__ val, const int *__restrict__ csr2sell,
+                                        double *__restrict__ sell_val, double *__restrict__ bval)
+{
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x) {
+        const int d = csr2sell[k];
+        const double v = val[k];
+        if (d >= 0) sell_val[d] = v; else bval[-d - 1] = v;
+    }
+}
+
+// PCSetUp_Jacobi (reciprocal diagonal, 0 -> 1) fused with the CG start: x = 0, r = b, z = M^-1 r, (z.z, z.r)
+__global__ void __launch_bounds__(CG_THREADS)
+cg_setup_kernel(int nloc, int row_lo, int pc_type, const int *__restrict__ rowptr, const int *__restrict__ col,
+                const double *__restrict__ val, const double *__restrict__ b, double *__restrict__ x,
+                double *__restrict__ r, double *__restrict__ z, double *__restrict__ dinv, double *__restrict__ partials,
+                int pstride, CgState *st, int finalize)
+{
+    __shared__ double sh[32];
+    double zz = 0.0, zr = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += gridDim.x * blockDim.x) {
+        double d = 0.0;
+        int lo = rowptr[i], hi = rowptr[i + 1];
+        const int end = hi, c = row_lo + i;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (col[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo < end && col[lo] == c) d = val[lo];
+        const double di = pc_type == PFEM_PC_JACOBI ? (d == 0.0 ? 1.0 : 1.0 / d) : 1.0;
+        const double ri = b[i], zi = ri * di;
+        dinv[i] = di; x[i] = 0.0; r[i] = ri; z[i] = zi;
+        zz += zi * zi; zr += zi * ri;
+    }
+    zz = block_sum(zz, sh);
+    zr = block_sum(zr, sh);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = zz; partials[pstride + blockIdx.x] = zr; }
+    if (last_block(&st->ticket[0])) {
+        const double a = reduce_partials(partials, gridDim.x, sh);
+        const double c = reduce_partials(partials + pstride, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            st->ticket[0] = 0;
+            if (finalize) step_after_setup(st, a, c);
+            else { st->red[0] = a; st->red[1] = c; }
+        }
+    }
+}
+
+// p = z + b p   (VecAYPX; p = z on the first iteration)
+__global__ void __launch_bounds__(CG_THREADS)
+cg_direction_kernel(int n, const double *__restrict__ z, double *__restrict__ p, const CgState *__restrict__ st)
+{
+    if (st->reason != 0) return;
+    const double b = st->b;
+    const bool first = st->iter == 0;
+    const int n2 = n >> 1;
+    const double2 *z2 = reinterpret_cast<const double2 *>(z);
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 zv = z2[i];
+        double2 pv;
+        if (first) pv = zv;
+        else { pv = p2[i]; pv.x = zv.x + b * pv.x; pv.y = zv.y + b * pv.y; }
+        p2[i] = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = first ? z[n - 1] : z[n - 1] + b * p[n - 1];
+}
+
+// w = A_diag p over SELL-32 slices (one warp per slice), fused with the local part of p.w
+__global__ void __launch_bounds__(CG_THREADS)
+spmv_sell_kernel(int nslices, int nloc, const long long *__restrict__ slice_off, const int *__restrict__ col,
+                 const double *__restrict__ val, const double *__restrict__ p, double *__restrict__ w,
+                 double *__restrict__ partials, CgState *st, int mode /*0: no dot, 1: dot + finalize, 2: dot, publish red*/)
+{
+    __shared__ double sh[32];
+    if (st && st->reason != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    double pw = 0.0;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += warps) {
+        const long long o0 = slice_off[s], o1 = slice_off[s + 1];
+        const int width = (int)((o1 - o0) >> 5);
+        const int *cp = col + o0 + lane;
+        const double *vp = val + o0 + lane;
+        double sum = 0.0;
+        int k = 0;
+        for (; k + 4 <= width; k += 4) {
+            const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32);
+            const int c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
+            const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32);
+            const double v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
+            const double x0 = __ldg(p + c0), x1 = __ldg(p + c1), x2 = __ldg(p + c2), x3 = __ldg(p + c3);
+            sum = fma(v0, x0, sum); sum = fma(v1, x1, sum); sum = fma(v2, x2, sum); sum = fma(v3, x3, sum);
+        }
+        for (; k < width; k++) sum = fma(__ldcs(vp + k * 32), __ldg(p + __ldcs(cp + k * 32)), sum);
+        const int r = s * 32 + lane;
+        if (r < nloc) {
+            w[r] = sum;
+            if (mode) pw = fma(__ldg(p + r), sum, pw);
+        }
+    }
+    if (!mode) return;
+    pw = block_sum(pw, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = pw;
+    if (last_block(&st->ticket[1])) {
+        const double t = reduce_partials(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            st->ticket[1] = 0;
+            if (mode == 1) step_after_spmv(st, t); else st->red[2] = t;
+        }
+    }
+}
+
+// w[brow] += B ghost (off-diagonal block, CSR over the boundary rows), plus its share of p.w; then publishes
+// red[0] = local p.w (diag + offdiag parts) for the all-reduce
+__global__ void __launch_bounds__(CG_THREADS)
+spmv_offdiag_kernel(int n_brows, const int *__restrict__ brow_ids, const int *__restrict__ brow_ptr,
+                    const int *__restrict__ bcol, const double *__restrict__ bval, const double *__restrict__ ghost,
+                    const double *__restrict__ p, double *__restrict__ w, double *__restrict__ partials, CgState *st)
+{
+    __shared__ double sh[32];
+    if (st->reason != 0) return;
+    double pw = 0.0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_brows; q += gridDim.x * blockDim.x) {
+        double sum = 0.0;
+        for (int k = brow_ptr[q]; k < brow_ptr[q + 1]; k++) sum = fma(bval[k], ghost[bcol[k]], sum);
+        const int r = brow_ids[q];
+        w[r] += sum;
+        pw = fma(p[r], sum, pw);
+    }
+    pw = block_sum(pw, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = pw;
+    if (last_block(&st->ticket[2])) {
+        const double t = reduce_partials(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) { st->ticket[2] = 0; st->red[0] = st->red[2] + t; }
+    }
+}
+
+__global__ void pack_halo_kernel(int n, const int *__restrict__ idx, const double *__restrict__ p, double *__restrict__ buf,
+                                 const CgState *__restrict__ st)
+{
+    if (st->reason != 0) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[i] = p[idx[i]];
+}
+
+// x += a p ; r -= a w ; z = M^-1 r ; partial (z.z, z.r)      (VecAXPY x2, PCApply_Jacobi, VecNorm, VecDot)
+__global__ void __launch_bounds__(CG_THREADS)
+cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__ w, const double *__restrict__ dinv,
+                 double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ partials,
+                 int pstride, CgState *st, int finalize)
+{
+    __shared__ double sh[32];
+    if (st->reason != 0) return;
+    const double a = st->a;
+    double zz = 0.0, zr = 0.0;
+    const int n2 = n >> 1;
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *w2 = reinterpret_cast<const double2 *>(w);
+    const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
+    double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r), *z2 = reinterpret_cast<double2 *>(z);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 pv = p2[i], wv = w2[i], dv = d2[i];
+        double2 xv = x2[i], rv = r2[i], zv;
+        xv.x = fma(a, pv.x, xv.x); xv.y = fma(a, pv.y, xv.y);
+        rv.x = fma(-a, wv.x, rv.x); rv.y = fma(-a, wv.y, rv.y);
+        zv.x = rv.x * dv.x; zv.y = rv.y * dv.y;
+        x2[i] = xv; r2[i] = rv; z2[i] = zv;
+        zz = fma(zv.x, zv.x, zz); zz = fma(zv.y, zv.y, zz);
+        zr = fma(zv.x, rv.x, zr); zr = fma(zv.y, rv.y, zr);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = n - 1;
+        const double xv = fma(a, p[i], x[i]), rv = fma(-a, w[i], r[i]), zv = rv * dinv[i];
+        x[i] = xv; r[i] = rv; z[i] = zv;
+        zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
+    }
+    zz = block_sum(zz, sh);
+    zr = block_sum(zr, sh);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = zz; partials[pstride + blockIdx.x] = zr; }
+    if (last_block(&st->ticket[3])) {
+        const double s0 = reduce_partials(partials, gridDim.x, sh);
+        const double s1 = reduce_partials(partials + pstride, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            st->ticket[3] = 0;
+            if (finalize) step_after_update(st, s0, s1);
+            else { st->red[0] = s0; st->red[1] = s1; }
+        }
+    }
+}
+
+static int grid_for(pfem_solver *h, long long work_items, int per_thread)
+{
+    long long blocks = (work_items + (long long)CG_THREADS * per_thread - 1) / ((long long)CG_THREADS * per_thread);
+    const long long cap = (long long)h->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+static int launch_spmv(pfem_solver *h, int mode)
+{
+    const int g = grid_for(h, (long long)h->A.nslices * 32, 1);
+    const bool prof = h->profile && mode > 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) {
+        PFEM_CUDA(cudaEventCreate(&e0));
+        PFEM_CUDA(cudaEventCreate(&e1));
+        h->prof_ev.push_back(e0);
+        h->prof_ev.push_back(e1);
+        PFEM_CUDA(cudaEventRecord(e0, h->stream));
+    }
+    spmv_sell_kernel<<<g, CG_THREADS, 0, h->stream>>>(h->A.nslices, h->size_local, h->A.slice_off.p, h->A.col.p,
+                                                      h->A.val.p, h->p.p, h->w.p, h->partials.p + 2 * h->sm_count * 16,
+                                                      mode >= 0 ? h->cg.p : nullptr, mode < 0 ? 0 : mode);
+    h->launches++;
+    if (prof) PFEM_CUDA(cudaEventRecord(e1, h->stream));
+    return PFEM_OK;
+}
+
+// sum the SpMV event pairs whose kernels actually ran (launches after convergence early-out in ~2 us: skip them)
+static int collect_profile(pfem_solver *h, int its)
+{
+    const size_t pairs = h->prof_ev.size() / 2;
+    for (size_t i = 0; i < pairs; i++) {
+        if ((int)i < its) {
+            float ms = 0.f;
+            PFEM_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+            h->prof_spmv_s += ms * 1e-3;
+            h->prof_spmv_n++;
+        }
+        cudaEventDestroy(h->prof_ev[2 * i]);
+        cudaEventDestroy(h->prof_ev[2 * i + 1]);
+    }
+    h->prof_ev.clear();
+    return PFEM_OK;
+}
+
+int cg_solve(pfem_solver *h)
+{
+    cudaStream_t s = h->stream;
+    const int nloc = h->size_local, P = h->nranks;
+    const int pstride = h->sm_count * 16;
+    const bool multi = P > 1;
+    PFEM_CUDA(cudaEventRecord(h->ev0, s));
+    // KSPSetUp: move the assembled values into the solver layout
+    if (h->nnz > 0) {
+        values_to_solver_kernel<<<grid_for(h, h->nnz, 4), CG_THREADS, 0, s>>>(h->nnz, h->val.p, h->csr2sell.p, h->A.val.p, h->bval.p);
+        h->launches++;
+    }
+    CgState init;
+    memset(&init, 0, sizeof init);
+    init.rtol = h->rtol; init.abstol = h->abstol; init.dtol = h->dtol; init.max_it = h->max_it;
+    init.iter = multi ? -1 : 0;
+    PFEM_CUDA(cudaMemcpyAsync(h->cg.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    const int gv = grid_for(h, nloc, 2);
+    cg_setup_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->row_lo, h->pc_type, h->rowptr.p, h->col.p, h->val.p, h->rhs.p, h->x.p,
+                                              h->r.p, h->z.p, h->dinv.p, h->partials.p, pstride, h->cg.p, multi ? 0 : 1);
+    h->launches++;
+    if (multi) {
+        PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 2, s));
+        scalar_after_setup_kernel<<<1, 1, 0, s>>>(h->cg.p);
+        h->launches++;
+    }
+    const int chunk = 16;
+    const int n_send = multi ? h->send_displs[P] : 0;
+    int reason = 0;
+    long long guard = 0;
+    while (true) {
+        for (int c = 0; c < chunk; c++) {
+            cg_direction_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->z.p, h->p.p, h->cg.p);
+            h->launches++;
+            if (!multi) {
+                PFEM_TRY(launch_spmv(h, 1));
+            } else {
+                // halo: pack boundary values, exchange on the comm stream while the diagonal block multiplies
+                if (n_send > 0) {
+                    pack_halo_kernel<<<grid_for(h, n_send, 1), CG_THREADS, 0, s>>>(n_send, h->send_idx.p, h->p.p, h->send_buf.p, h->cg.p);
+                    h->launches++;
+                }
+                PFEM_CUDA(cudaEventRecord(h->ev_pack, s));
+                PFEM_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+                PFEM_TRY(comm_halo_exchange(h, h->send_buf.p, h->ghost_buf.p, h->comm_stream));
+                PFEM_CUDA(cudaEventRecord(h->ev_halo, h->comm_stream));
+                PFEM_TRY(launch_spmv(h, 2));
+                PFEM_CUDA(cudaStreamWaitEvent(s, h->ev_halo, 0));
+                spmv_offdiag_kernel<<<grid_for(h, h->n_brows > 0 ? h->n_brows : 1, 1), CG_THREADS, 0, s>>>(
+                    h->n_brows, h->brow_ids.p, h->brow_ptr.p, h->bcol.p, h->bval.p, h->ghost_buf.p, h->p.p, h->w.p,
+                    h->partials.p + 3 * pstride, h->cg.p);
+                h->launches++;
+                PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 1, s));
+                scalar_after_spmv_kernel<<<1, 1, 0, s>>>(h->cg.p);
+                h->launches++;
+            }
+            cg_update_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->p.p, h->w.p, h->dinv.p, h->x.p, h->r.p, h->z.p, h->partials.p,
+                                                       pstride, h->cg.p, multi ? 0 : 1);
+            h->launches++;
+            if (multi) {
+                PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 2, s));
+                scalar_after_update_kernel<<<1, 1, 0, s>>>(h->cg.p);
+                h->launches++;
+            }
+        }
+        PFEM_CUDA(cudaMemcpyAsync(h->cg_host, h->cg.p, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        reason = h->cg_host->reason;
+        if (reason != 0) break;
+        guard += chunk;
+        if (guard > (long long)h->max_it + 2 * chunk) { set_error("cg: iteration guard tripped"); return PFEM_ERR_STATE; }
+    }
+    PFEM_CUDA(cudaEventRecord(h->ev1, s));
+    PFEM_CUDA(cudaEventSynchronize(h->ev1));
+    PFEM_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    PFEM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->t_solve = ms * 1e-3;
+    h->its = h->cg_host->its; h->reason = reason; h->rnorm = h->cg_host->dp;
+    if (h->profile) PFEM_TRY(collect_profile(h, h->its));
+    return PFEM_OK;
+}
+
+int time_spmv(pfem_solver *h, int reps, double *seconds)
+{
+    if (reps < 1) reps = 1;
+    cudaStream_t s = h->stream;
+    if (h->nnz > 0) {
+        values_to_solver_kernel<<<grid_for(h, h->nnz, 4), CG_THREADS, 0, s>>>(h->nnz, h->val.p, h->csr2sell.p, h->A.val.p, h->bval.p);
+        h->launches++;
+    }
+    PFEM_CUDA(cudaMemcpyAsync(h->p.p, h->rhs.p, (size_t)h->size_local * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < 3; i++) PFEM_TRY(launch_spmv(h, -1));
+    PFEM_CUDA(cudaEventRecord(h->ev0, s));
+    for (int i = 0; i < reps; i++) PFEM_TRY(launch_spmv(h, -1));
+    PFEM_CUDA(cudaEventRecord(h->ev1, s));
+    PFEM_CUDA(cudaEventSynchronize(h->ev1));
+    PFEM_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    PFEM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    *seconds = ms * 1e-3 / reps;
+    return PFEM_OK;
+}
+
+}  // namespace pfem

@@ -1,0 +1,176 @@
+// internal.cuh -- solver handle and cross-TU declarations of libpfemb200.so (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pfem_b200.h"
+
+namespace pfem {
+
+void set_error(const char *fmt, ...);
+
+#define PFEM_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            pfem::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return PFEM_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define PFEM_TRY(call)                  \
+    do {                                \
+        int s_ = (call);                \
+        if (s_ != PFEM_OK) return s_;   \
+    } while (0)
+
+// Simple owning device buffer.
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return PFEM_ERR_CUDA;
+        }
+        n = count;
+        return PFEM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// Device-resident CG scalar state (one per solver).  Kernels early-out when reason != 0.
+struct CgState {
+    double beta, betaold, dpi, dpiold, dp, a, b, ttol, rnorm0;
+    double rtol, abstol, dtol;
+    double red[4];          // reduction landing zone (local sums; all-reduced in place for nranks > 1)
+    int its, reason, iter, max_it;
+    unsigned int ticket[4]; // last-block-done counters
+};
+
+struct NcclApi;             // comm.cu
+
+// SELL-32 storage of the diagonal block (columns owned by this rank), built at pattern time.
+struct SellMatrix {
+    int nrows = 0, nslices = 0;
+    long long nstored = 0;                    // padded entries
+    DevBuf<long long> slice_off;              // [nslices+1] offsets (in entries)
+    DevBuf<int> col;                          // [nstored] local column index
+    DevBuf<double> val;                       // [nstored]
+};
+
+}  // namespace pfem
+
+struct pfem_solver {
+    int device = 0, rank = 0, nranks = 1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_pack = nullptr;
+    int state = PFEM_SOLVER_EMPTY;
+    bool initialised = false;
+    long long launches = 0;
+
+    // sizes (solverpetsc.F:116-131)
+    int size_local = 0, size_global = 0, row_lo = 0, row_hi = 0;   // owned rows [row_lo,row_hi), 0-based
+    std::vector<int> row_starts;                                   // [nranks+1]
+
+    // options
+    double rtol = 1e-5, abstol = 1e-50, dtol = 1e4;
+    int max_it = 10000, pc_type = PFEM_PC_JACOBI;
+
+    // mesh resident in HBM
+    int kind = -1, npe = 0, ndof = 0, ndim = 0, nsize = 0;
+    int nElem = 0, nNode = 0;
+    int rec_ints = 0;                                              // ints per element record
+    pfem::DevBuf<int> erec;        // AoS per element: conn[npe] (0-based NEW node id) then dof[nsize], padded to rec_ints
+    pfem::DevBuf<double> xyz;      // AoS per NEW node: (x,y[,z,pad])
+    pfem::DevBuf<double> applied;  // solnApplied, NEW numbering
+    bool have_mesh = false, have_dofs = false;
+
+    // pattern (owned rows, global columns)
+    long long nnz = 0, ninc = 0;
+    pfem::DevBuf<int> rowptr, col;
+    pfem::DevBuf<double> val, rhs;
+    pfem::DevBuf<int> rinc_ptr, rinc;      // row -> (e*nsize + k) incidences, ascending
+    bool values_zero = true, rhs_zero = true;
+    int asm_rows_per_cta = 0, asm_max_seg = 0;
+    size_t asm_smem = 0;
+    pfem::DevBuf<int> neg_count;
+
+    // solver
+    pfem::SellMatrix A;                    // diagonal block
+    // off-diagonal block (ghost columns), CSR over the boundary rows only
+    int n_ghost = 0, n_brows = 0;
+    long long nnz_off = 0;
+    pfem::DevBuf<int> brow_ids, brow_ptr, bcol;   // boundary row ids (local), ptr, compact ghost index
+    pfem::DevBuf<double> bval;
+    pfem::DevBuf<int> csr2sell;            // per CSR slot: destination (>=0 SELL entry, <0: -(offdiag entry)-1)
+    std::vector<int> ghost_cols;           // global ids (sorted): PETSc garray
+    // halo plan
+    std::vector<int> send_counts, recv_counts, send_displs, recv_displs;
+    pfem::DevBuf<int> send_idx;            // local row indices to pack, grouped by destination rank
+    pfem::DevBuf<double> send_buf, ghost_buf;
+    pfem::DevBuf<double> x, r, z, p, w, dinv;
+    pfem::DevBuf<double> partials;         // [4][max_blocks]
+    pfem::DevBuf<pfem::CgState> cg;
+    pfem::CgState *cg_host = nullptr;      // pinned mirror
+    int its = 0, reason = 0;
+    double rnorm = 0.0, t_assemble = 0.0, t_solve = 0.0;
+    // optional per-launch timing of the SpMV inside the solve (bench roofline evidence)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    double prof_spmv_s = 0.0;
+    long long prof_spmv_n = 0;
+
+    // communicator
+    pfem::NcclApi *nccl = nullptr;
+    void *comm = nullptr;
+};
+
+namespace pfem {
+
+// elements.cu
+int element_ke_batch(int kind, int n, const double *x, const double *y, const double *z, const double *elemData,
+                     const double *timeData, const double *valC, double *K, double *F, int *jac_neg);
+// pattern.cu
+int upload_mesh(pfem_solver *h, int kind, int nElem, const int *conn, int nNode, const double *coords,
+                const int *node_map_get_old);
+int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof);
+// assembly.cu
+int plan_assembly(pfem_solver *h);
+int assemble_values(pfem_solver *h, const double *elemData, const double *timeData, int *n_neg);
+int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const double *vals, bool transposed,
+                const double *F);
+// cg.cu
+int build_solver_structures(pfem_solver *h);
+int cg_solve(pfem_solver *h);
+int time_spmv(pfem_solver *h, int reps, double *seconds);
+// comm.cu
+int comm_unique_id(void *id128);
+int comm_init(pfem_solver *h, const void *id128);
+void comm_destroy(pfem_solver *h);
+int comm_allgather_int(pfem_solver *h, int value, std::vector<int> &out);
+int comm_alltoallv_int(pfem_solver *h, const std::vector<int> &sendbuf, const std::vector<int> &sendcounts,
+                       std::vector<int> &recvbuf, std::vector<int> &recvcounts);
+int comm_halo_exchange(pfem_solver *h, const double *sendbuf, double *recvbuf, cudaStream_t s);
+int comm_allreduce_sum(pfem_solver *h, double *buf, int n, cudaStream_t s);
+int comm_allgatherv_double(pfem_solver *h, const double *local, double *global_dev, cudaStream_t s);
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace pfem

@@ -1,0 +1,332 @@
+// pattern.cu -- mesh upload and the pattern pass on the GPU.
+//
+// Replaces the MatSetValues(INSERT_VALUES, zeros) loop + MatAssembly of the reference
+// (tetrapoissonparallelimpl1.F:791-802, solverpetsc.F:222-246): the CSR pattern of the owned rows is
+// built from the element dof lists only (never from values: explicit zeros are part of the pattern),
+// with sorted unique global columns per row, which is what PETSc's AIJ stores after final assembly.
+// Also builds the row -> element incidence lists (ascending element id) that the value pass gathers from.
+#include <cub/cub.cuh>
+
+#include "internal.cuh"
+
+namespace pfem {
+
+// ---- mesh upload ---------------------------------------------------------------------------------
+
+// erec[e] = { conn[0..npe) 0-based, dof[0..nsize), pad }, SoA -> AoS (one 32/64-byte record per element)
+__global__ void pack_conn_kernel(int nElem, int npe, int rec_ints, const int *__restrict__ conn_soa, int *__restrict__ erec)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)nElem * npe;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / nElem), e = (int)(t - (long long)i * nElem);   // coalesced read of the SoA column
+        erec[(size_t)e * rec_ints + i] = conn_soa[t] - 1;
+    }
+}
+
+__global__ void pack_dof_kernel(int nElem, int npe, int nsize, int rec_ints, const int *__restrict__ dof_soa,
+                                int *__restrict__ erec)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)nElem * nsize;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / nElem), e = (int)(t - (long long)k * nElem);
+        erec[(size_t)e * rec_ints + npe + k] = dof_soa[t];
+    }
+}
+
+// xyz[n_new] = coords(node_map_get_old(n_new), :)   (tetrapoissonparallelimpl1.F:832-838)
+__global__ void pack_xyz_kernel(int nNode, int ndim, int stride, const double *__restrict__ coords_soa,
+                                const int *__restrict__ map_old, double *__restrict__ xyz)
+{
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < nNode; n += gridDim.x * blockDim.x) {
+        const int o = map_old ? map_old[n] - 1 : n;
+        for (int c = 0; c < stride; c++) xyz[(size_t)n * stride + c] = c < ndim ? coords_soa[(size_t)c * nNode + o] : 0.0;
+    }
+}
+
+__global__ void check_range_kernel(long long n, const int *__restrict__ v, int lo, int hi, int *__restrict__ bad)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        if (v[t] < lo || v[t] >= hi) atomicAdd(bad, 1);
+}
+
+static int kind_dims(int kind, int &npe, int &ndof, int &ndim)
+{
+    switch (kind) {
+    case PFEM_POISSON_TRIA: npe = 3; ndof = 1; ndim = 2; return PFEM_OK;
+    case PFEM_POISSON_TETRA: npe = 4; ndof = 1; ndim = 3; return PFEM_OK;
+    case PFEM_ELASTICITY_TRIA: npe = 3; ndof = 2; ndim = 2; return PFEM_OK;
+    case PFEM_ELASTICITY_TETRA: npe = 4; ndof = 3; ndim = 3; return PFEM_OK;
+    }
+    set_error("unknown element kind %d", kind);
+    return PFEM_ERR_ARG;
+}
+
+int upload_mesh(pfem_solver *h, int kind, int nElem, const int *conn, int nNode, const double *coords,
+                const int *node_map_get_old)
+{
+    int npe, ndof, ndim;
+    PFEM_TRY(kind_dims(kind, npe, ndof, ndim));
+    if (nElem <= 0 || nNode <= 0 || !conn || !coords) { set_error("pfem_solver_set_mesh: bad argument"); return PFEM_ERR_ARG; }
+    const int nsize = npe * ndof;
+    if ((long long)nElem * nsize >= (1LL << 31)) { set_error("nElem*nsize exceeds 2^31"); return PFEM_ERR_SIZE; }
+    h->kind = kind; h->npe = npe; h->ndof = ndof; h->ndim = ndim; h->nsize = nsize;
+    h->nElem = nElem; h->nNode = nNode;
+    h->rec_ints = ((npe + nsize + 3) / 4) * 4;
+    h->have_mesh = false; h->have_dofs = false;
+    cudaStream_t s = h->stream;
+    PFEM_TRY(h->erec.alloc((size_t)nElem * h->rec_ints));
+    PFEM_CUDA(cudaMemsetAsync(h->erec.p, 0xFF, (size_t)nElem * h->rec_ints * sizeof(int), s));
+    {
+        DevBuf<int> tmp;
+        PFEM_TRY(tmp.alloc((size_t)nElem * npe));
+        PFEM_CUDA(cudaMemcpyAsync(tmp.p, conn, (size_t)nElem * npe * sizeof(int), cudaMemcpyHostToDevice, s));
+        DevBuf<int> bad;
+        PFEM_TRY(bad.alloc(1));
+        PFEM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+        check_range_kernel<<<h->sm_count * 8, 256, 0, s>>>((long long)nElem * npe, tmp.p, 1, nNode + 1, bad.p);
+        pack_conn_kernel<<<h->sm_count * 8, 256, 0, s>>>(nElem, npe, h->rec_ints, tmp.p, h->erec.p);
+        h->launches += 2;
+        int nbad = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        if (nbad) { set_error("pfem_solver_set_mesh: %d connectivity entries outside 1..nNode", nbad); return PFEM_ERR_ARG; }
+    }
+    {
+        const int stride = ndim == 3 ? 4 : 2;
+        DevBuf<double> tmp;
+        DevBuf<int> map;
+        PFEM_TRY(tmp.alloc((size_t)nNode * ndim));
+        PFEM_CUDA(cudaMemcpyAsync(tmp.p, coords, (size_t)nNode * ndim * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (node_map_get_old) {
+            PFEM_TRY(map.alloc(nNode));
+            PFEM_CUDA(cudaMemcpyAsync(map.p, node_map_get_old, (size_t)nNode * sizeof(int), cudaMemcpyHostToDevice, s));
+            DevBuf<int> bad;
+            PFEM_TRY(bad.alloc(1));
+            PFEM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+            check_range_kernel<<<h->sm_count * 4, 256, 0, s>>>(nNode, map.p, 1, nNode + 1, bad.p);
+            h->launches++;
+            int nbad = 0;
+            PFEM_CUDA(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            PFEM_CUDA(cudaStreamSynchronize(s));
+            if (nbad) { set_error("pfem_solver_set_mesh: node_map_get_old outside 1..nNode"); return PFEM_ERR_ARG; }
+        }
+        PFEM_TRY(h->xyz.alloc((size_t)nNode * stride));
+        pack_xyz_kernel<<<h->sm_count * 4, 256, 0, s>>>(nNode, ndim, stride, tmp.p, node_map_get_old ? map.p : nullptr, h->xyz.p);
+        h->launches++;
+        PFEM_CUDA(cudaGetLastError());
+        PFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    PFEM_TRY(h->applied.alloc((size_t)nNode * ndof));
+    PFEM_CUDA(cudaMemsetAsync(h->applied.p, 0, (size_t)nNode * ndof * sizeof(double), s));
+    h->have_mesh = true;
+    return PFEM_OK;
+}
+
+// ---- incidence lists -------------------------------------------------------------------------------
+
+// key = owned local row of the dof at code = e*nsize+k, or the sentinel nloc (sorted to the end)
+__global__ void inc_keys_kernel(long long total, int nsize, int npe, int rec_ints, const int *__restrict__ erec,
+                                int row_lo, int row_hi, int *__restrict__ keys, int *__restrict__ vals)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(t / nsize), k = (int)(t - (long long)e * nsize);
+        const int d = erec[(size_t)e * rec_ints + npe + k];
+        keys[t] = (d >= row_lo && d < row_hi) ? d - row_lo : row_hi - row_lo;
+        vals[t] = (int)t;
+    }
+}
+
+// ptr[r] = lower_bound(keys_sorted, r) for r = 0..nloc
+__global__ void lower_bound_kernel(int nloc, long long total, const int *__restrict__ keys, int *__restrict__ ptr)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= nloc; r += gridDim.x * blockDim.x) {
+        long long lo = 0, hi = total;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (keys[mid] < r) lo = mid + 1; else hi = mid;
+        }
+        ptr[r] = (int)lo;
+    }
+}
+
+// upper bound on the row length: sum over incident elements of their free-dof count
+__global__ void cand_count_kernel(int nloc, int nsize, int npe, int rec_ints, const int *__restrict__ erec,
+                                  const int *__restrict__ rinc_ptr, const int *__restrict__ rinc,
+                                  long long *__restrict__ cand)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += gridDim.x * blockDim.x) {
+        long long c = 0;
+        for (int m = rinc_ptr[r]; m < rinc_ptr[r + 1]; m++) {
+            const int e = rinc[m] / nsize;
+            const int *dof = erec + (size_t)e * rec_ints + npe;
+            for (int j = 0; j < nsize; j++) c += dof[j] >= 0;
+        }
+        cand[r] = c;
+    }
+}
+
+// per-row sorted-unique insertion of the candidate columns into scratch[cand_off[r] ...]
+__global__ void row_unique_kernel(int nloc, int nsize, int npe, int rec_ints, const int *__restrict__ erec,
+                                  const int *__restrict__ rinc_ptr, const int *__restrict__ rinc,
+                                  const long long *__restrict__ cand_off, int *__restrict__ scratch,
+                                  int *__restrict__ rowlen)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nloc; r += gridDim.x * blockDim.x) {
+        int *s = scratch + cand_off[r];
+        int len = 0;
+        for (int m = rinc_ptr[r]; m < rinc_ptr[r + 1]; m++) {
+            const int e = rinc[m] / nsize;
+            const int *dof = erec + (size_t)e * rec_ints + npe;
+            for (int j = 0; j < nsize; j++) {
+                const int c = dof[j];
+                if (c < 0) continue;
+                int lo = 0, hi = len;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s[mid] < c) lo = mid + 1; else hi = mid;
+                }
+                if (lo < len && s[lo] == c) continue;
+                for (int t = len; t > lo; t--) s[t] = s[t - 1];
+                s[lo] = c;
+                len++;
+            }
+        }
+        rowlen[r] = len;
+    }
+}
+
+__global__ void sum_int_kernel(int n, const int *__restrict__ v, unsigned long long *__restrict__ out)
+{
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)v[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+__global__ void compact_cols_kernel(int nloc, const long long *__restrict__ cand_off, const int *__restrict__ scratch,
+                                    const int *__restrict__ rowptr, int *__restrict__ col)
+{
+    // one warp per row
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nloc; r += warps) {
+        const int a = rowptr[r], n = rowptr[r + 1] - a;
+        const int *s = scratch + cand_off[r];
+        for (int k = lane; k < n; k += 32) col[a + k] = s[k];
+    }
+}
+
+int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
+{
+    if (!h->initialised) { set_error("pfem_solver_set_pattern: call pfem_solver_initialise first"); return PFEM_ERR_STATE; }
+    if (!h->have_mesh) { set_error("pfem_solver_set_pattern: call pfem_solver_set_mesh first"); return PFEM_ERR_STATE; }
+    if (nElem != h->nElem || nsize != h->nsize || !elemDof) {
+        set_error("pfem_solver_set_pattern: nElem/nsize (%d,%d) do not match the mesh (%d,%d)", nElem, nsize, h->nElem, h->nsize);
+        return PFEM_ERR_ARG;
+    }
+    cudaStream_t s = h->stream;
+    const int G = h->sm_count * 8;
+    const int nloc = h->size_local;
+    const long long total = (long long)nElem * nsize;
+    // 1. element dof records
+    {
+        DevBuf<int> tmp, bad;
+        PFEM_TRY(tmp.alloc((size_t)total));
+        PFEM_TRY(bad.alloc(1));
+        PFEM_CUDA(cudaMemcpyAsync(tmp.p, elemDof, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s));
+        PFEM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+        check_range_kernel<<<G, 256, 0, s>>>(total, tmp.p, -1, h->size_global, bad.p);
+        pack_dof_kernel<<<G, 256, 0, s>>>(nElem, h->npe, nsize, h->rec_ints, tmp.p, h->erec.p);
+        h->launches += 2;
+        int nbad = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        if (nbad) { set_error("pfem_solver_set_pattern: %d dof ids outside -1..size_global-1", nbad); return PFEM_ERR_NUMBERING; }
+    }
+    h->have_dofs = true;
+    // 2. row -> incidence lists: stable radix sort of (local row, e*nsize+k); ties keep ascending code order
+    PFEM_TRY(h->rinc_ptr.alloc((size_t)nloc + 1));
+    {
+        DevBuf<int> k_in, k_out, v_in, v_out;
+        PFEM_TRY(k_in.alloc((size_t)total));
+        PFEM_TRY(k_out.alloc((size_t)total));
+        PFEM_TRY(v_in.alloc((size_t)total));
+        PFEM_TRY(v_out.alloc((size_t)total));
+        inc_keys_kernel<<<G, 256, 0, s>>>(total, nsize, h->npe, h->rec_ints, h->erec.p, h->row_lo, h->row_hi, k_in.p, v_in.p);
+        h->launches++;
+        int bits = 1;
+        while ((1LL << bits) <= nloc) bits++;
+        size_t tmp_bytes = 0;
+        PFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, total, 0, bits, s));
+        DevBuf<char> tmp;
+        PFEM_TRY(tmp.alloc(tmp_bytes));
+        PFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, total, 0, bits, s));
+        lower_bound_kernel<<<G, 256, 0, s>>>(nloc, total, k_out.p, h->rinc_ptr.p);
+        h->launches += 2;
+        int ninc = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&ninc, h->rinc_ptr.p + nloc, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        h->ninc = ninc;
+        PFEM_TRY(h->rinc.alloc((size_t)ninc));
+        PFEM_CUDA(cudaMemcpyAsync(h->rinc.p, v_out.p, (size_t)ninc * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    // 3. pattern: per-row sorted unique columns
+    {
+        DevBuf<long long> cand, cand_off;
+        DevBuf<int> rowlen;
+        PFEM_TRY(cand.alloc((size_t)nloc + 1));
+        PFEM_TRY(cand_off.alloc((size_t)nloc + 1));
+        PFEM_TRY(rowlen.alloc((size_t)nloc + 1));
+        PFEM_CUDA(cudaMemsetAsync(cand.p, 0, ((size_t)nloc + 1) * sizeof(long long), s));
+        PFEM_CUDA(cudaMemsetAsync(rowlen.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
+        cand_count_kernel<<<G, 256, 0, s>>>(nloc, nsize, h->npe, h->rec_ints, h->erec.p, h->rinc_ptr.p, h->rinc.p, cand.p);
+        h->launches++;
+        size_t tmp_bytes = 0, tmp_bytes2 = 0;
+        PFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cand.p, cand_off.p, nloc + 1, s));
+        PFEM_TRY(h->rowptr.alloc((size_t)nloc + 1));
+        PFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes2, rowlen.p, h->rowptr.p, nloc + 1, s));
+        DevBuf<char> tmp;
+        PFEM_TRY(tmp.alloc(tmp_bytes > tmp_bytes2 ? tmp_bytes : tmp_bytes2));
+        PFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cand.p, cand_off.p, nloc + 1, s));
+        h->launches++;
+        long long ncand = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&ncand, cand_off.p + nloc, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        DevBuf<int> scratch;
+        PFEM_TRY(scratch.alloc((size_t)ncand));
+        row_unique_kernel<<<G, 128, 0, s>>>(nloc, nsize, h->npe, h->rec_ints, h->erec.p, h->rinc_ptr.p, h->rinc.p,
+                                            cand_off.p, scratch.p, rowlen.p);
+        h->launches++;
+        // nnz must fit the 32-bit rowptr: reduce in 64 bits first
+        DevBuf<long long> nnz64;
+        PFEM_TRY(nnz64.alloc(1));
+        PFEM_CUDA(cudaMemsetAsync(nnz64.p, 0, sizeof(long long), s));
+        sum_int_kernel<<<G, 256, 0, s>>>(nloc, rowlen.p, (unsigned long long *)nnz64.p);
+        h->launches++;
+        long long nnz = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&nnz, nnz64.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        if (nnz >= (1LL << 31)) { set_error("pattern has %lld nonzeros on this rank: exceeds 2^31", nnz); return PFEM_ERR_SIZE; }
+        PFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes2, rowlen.p, h->rowptr.p, nloc + 1, s));
+        h->launches++;
+        h->nnz = nnz;
+        PFEM_TRY(h->col.alloc((size_t)nnz));
+        PFEM_TRY(h->val.alloc((size_t)nnz));
+        PFEM_TRY(h->rhs.alloc((size_t)nloc));
+        compact_cols_kernel<<<G, 256, 0, s>>>(nloc, cand_off.p, scratch.p, h->rowptr.p, h->col.p);
+        h->launches++;
+        PFEM_CUDA(cudaMemsetAsync(h->val.p, 0, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double), s));
+        PFEM_CUDA(cudaMemsetAsync(h->rhs.p, 0, (size_t)(nloc > 0 ? nloc : 1) * sizeof(double), s));
+        PFEM_CUDA(cudaGetLastError());
+        PFEM_CUDA(cudaStreamSynchronize(s));
+    }
+    h->values_zero = true;
+    h->rhs_zero = true;
+    PFEM_TRY(h->neg_count.alloc(1));
+    h->asm_rows_per_cta = 0;
+    PFEM_TRY(plan_assembly(h));
+    return PFEM_OK;
+}
+
+}  // namespace pfem

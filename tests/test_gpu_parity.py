@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): pattern bit-exact; matrix/RHS values within 1e-12 relative (we assert the
+stronger bit-exact equality against the no-FMA oracle, and 1e-12 as the stated contract); CG iteration
+counts within +-2 %; solution within the KSP tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from pfemfort_b200 import driver as D, mesh as M, solver as S
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [S.POISSON_TRIA, S.POISSON_TETRA, S.ELASTICITY_TRIA, S.ELASTICITY_TETRA]
+REL_TOL_VALUES = 1e-12          # north_star tolerance for assembled values
+ITS_TOL = 0.02                  # +-2 % iteration count
+
+
+def _rand_elems(kind, n, seed):
+    rng = np.random.default_rng(seed)
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    if ndim == 2:
+        base = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    else:   # reference ordering: local node 3 is the origin of the parametric map
+        base = np.array([[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
+    xyz = base[:, :, None] + 0.2 * rng.standard_normal((ndim, npe, n)) + 3.0 * rng.standard_normal((ndim, 1, n))
+    return xyz
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_element_batch_bit_exact(gpu, kind):
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    n = 257
+    xyz = _rand_elems(kind, n, 1234 + kind)
+    elemData = {0: [1.3, 0.7], 1: [1.3, 0.7, 2.1], 2: [240.565, 0.3, 0.5, 0.1, -0.2],
+                3: [float(np.float32(240.565)), float(np.float32(0.3)), 1.0, float(np.float32(0.1)), 0.05, -0.3]}[kind]
+    timeData = [0.0, 0.9, 0.0]
+    rng = np.random.default_rng(99)
+    valC = rng.standard_normal((npe * ndof, n)) if ndof == 1 else None
+    K, F, neg = S.element_ke_batch(kind, xyz[0], xyz[1], xyz[2] if ndim == 3 else None, elemData, timeData, valC)
+    for e in range(n):
+        Ko, Fo, rc = O.element_ke(kind, xyz[0, :, e], xyz[1, :, e], xyz[2, :, e] if ndim == 3 else None, elemData, timeData,
+                                  valC[:, e] if valC is not None else None)
+        assert rc == neg[e]
+        if rc:
+            continue
+        assert np.array_equal(K[:, :, e], Ko), f"K differs for element {e}"
+        assert np.array_equal(F[:, e], Fo), f"F differs for element {e}"
+    assert (neg == 0).sum() > n // 2
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_single_element_entry_points(gpu, kind):
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    xyz = _rand_elems(kind, 1, 7)[:, :, 0]
+    elemData = [2.0, 0.25, 1.5, 0.1, 0.2, 0.3][: {0: 2, 1: 3, 2: 5, 3: 6}[kind]]
+    K, F = S.element_ke(kind, xyz[0], xyz[1], xyz[2] if ndim == 3 else None, elemData, [0, 1, 0])
+    Ko, Fo, rc = O.element_ke(kind, xyz[0], xyz[1], xyz[2] if ndim == 3 else None, elemData, [0, 1, 0])
+    assert rc == 0 and np.array_equal(K, Ko) and np.array_equal(F, Fo)
+    # negative Jacobian -> error code where the reference STOPs
+    sw = xyz.copy()
+    sw[:, [0, 1]] = sw[:, [1, 0]]
+    with pytest.raises(S.PfemError) as ei:
+        S.element_ke(kind, sw[0], sw[1], sw[2] if ndim == 3 else None, elemData, [0, 1, 0])
+    assert ei.value.status == S.ERR_NEG_JACOBIAN
+
+
+def _load(name, input_dir):
+    if name == "beam3Dtet6366":
+        return M.read_mesh(os.path.join(input_dir, name), swap_34=True), S.ELASTICITY_TETRA
+    kind = {"tria20x20": S.POISSON_TRIA, "tet10": S.POISSON_TETRA, "cookmembranetria32": S.ELASTICITY_TRIA}[name]
+    return M.read_mesh(os.path.join(input_dir, name)), kind
+
+
+def _oracle_system(m, kind, num, fbc=True):
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    rp, col = O.pattern(num.elemDof, num.size_global)
+    val, rhs, nbad = O.assemble(kind, num.conn_new, m.coords, num.node_map_get_old, num.elemDof, num.solnApplied,
+                                D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, rp, col)
+    assert nbad == 0
+    if fbc and m.fbc_node.size:
+        O.add_force_bc(rhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, num.node_map_get_new, num.NodeDofArrayNew, num.size_global)
+    return rp, col, val, rhs
+
+
+@pytest.mark.parametrize("name", ["tria20x20", "tet10", "cookmembranetria32", "beam3Dtet6366"])
+def test_fixture_assembly_and_solve(gpu, input_dir, name):
+    m, kind = _load(name, input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    info = D.run_rank(s, m, num, rtol=1e-10)
+    rp, col, val = s.get_csr()
+    rhs = s.get_rhs()
+    x = s.get_solution()
+    orp, ocol, oval, orhs = _oracle_system(m, kind, num)
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol)                 # pattern: bit-exact
+    scale = np.abs(oval).max()
+    assert np.abs(val - oval).max() <= REL_TOL_VALUES * scale                    # contract
+    assert np.array_equal(val, oval), "values not bit-identical to the no-FMA oracle"
+    assert np.array_equal(rhs, orhs)
+    ox, oits, oreason, ornorm = O.cg_jacobi(orp, ocol, oval, orhs, rtol=1e-10)
+    assert info["reason"] == oreason == 2
+    assert abs(info["its"] - oits) <= max(1, ITS_TOL * oits), (info["its"], oits)
+    assert np.abs(x - ox).max() <= 1e-7 * np.abs(ox).max()
+    s.free()
+
+
+def test_known_answers(gpu, input_dir):
+    """The analytic solutions baked into the reference's BC files."""
+    m, kind = _load("tria20x20", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    D.run_rank(s, m, num, rtol=1e-10)
+    u = D.nodal_solution(num, s.get_solution())[0]
+    exact = M.exact_poisson_tria(m.coords[0], m.coords[1])
+    assert abs(np.abs(u - exact).max() - 7.1146e-4) < 1e-6
+    s.free()
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    D.run_rank(s, m, num, rtol=1e-10)
+    u = D.nodal_solution(num, s.get_solution())[0]
+    assert np.abs(u - (m.coords ** 2).sum(0)).max() < 2e-7
+    s.free()
+
+
+def test_state_machine_and_slow_path(gpu, input_dir):
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    s.initialise(num.size_global, num.size_global)
+    with pytest.raises(S.PfemError) as ei:
+        s.setZero()
+    assert ei.value.status == S.ERR_STATE
+    s.set_mesh(kind, num.conn_new, m.coords)
+    s.set_pattern(num.elemDof)
+    with pytest.raises(S.PfemError) as ei:
+        s.factorise()                       # "Assemble matrix first before solving it!"
+    assert ei.value.status == S.ERR_STATE
+    with pytest.raises(S.PfemError) as ei:
+        s.solve()                           # "Factorise matrix first before solving it!"
+    assert ei.value.status == S.ERR_STATE
+    # per-element MatSetValues / VecSetValues mirrors reproduce the batched value pass
+    s.setZero()
+    ed, td = D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA
+    nE = 40
+    for e in range(nE):
+        nodes = num.conn_new[:, e] - 1
+        K, F, rc = O.element_ke(kind, m.coords[0, nodes], m.coords[1, nodes], m.coords[2, nodes], ed, td)
+        dofs = num.elemDof[:, e]
+        s.add_matrix(dofs, dofs, K)
+        for ii in range(4):
+            if dofs[ii] == -1:
+                for jj in range(4):
+                    if dofs[jj] != -1:
+                        F[jj] = F[jj] - K[jj, ii] * num.solnApplied[nodes[ii]]
+        s.add_vector(dofs, F)
+    rp, col, val = s.get_csr()
+    rhs = s.get_rhs()
+    mask = np.zeros(m.nElem, np.uint8)
+    mask[:nE] = 1
+    oval, orhs, _ = O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied, ed, td, rp, col, elem_mask=mask)
+    assert np.array_equal(val, oval) and np.array_equal(rhs, orhs)
+    s.free()
+
+
+def test_accumulate_without_set_zero_and_determinism(gpu, input_dir):
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    D.run_rank(s, m, num, do_solve=False)
+    _, _, v1 = s.get_csr()
+    r1 = s.get_rhs()
+    s.assemble(D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA)      # ADD on top, like a second MatSetValues sweep
+    _, _, v2 = s.get_csr()
+    rp, col = O.pattern(num.elemDof, num.size_global)
+    oval, orhs, _ = O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied,
+                               D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, rp, col)
+    oval, orhs, _ = O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied,
+                               D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, rp, col, val=oval, rhs=orhs)
+    assert np.array_equal(v2, oval) and np.array_equal(s.get_rhs(), orhs)
+    s.setZero()
+    s.assemble(D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA)
+    _, _, v3 = s.get_csr()
+    assert np.array_equal(v3, v1) and np.array_equal(s.get_rhs(), r1)   # run-to-run bit-identical
+    s.free()
+
+
+def test_negative_jacobian_is_reported(gpu, input_dir):
+    m = M.read_mesh(os.path.join(input_dir, "beam3Dtet6366"))          # as shipped: all 7776 Jacobians negative
+    num = D.number(m, S.ELASTICITY_TETRA)
+    s = S.SolverB200(0)
+    with pytest.raises(S.PfemError) as ei:
+        D.run_rank(s, m, num)
+    assert ei.value.status == S.ERR_NEG_JACOBIAN
+    s.free()
+
+
+def test_zero_rhs_converges_at_iteration_zero(gpu, input_dir):
+    m, kind = _load("cookmembranetria32", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    info = D.run_rank(s, m, num, apply_force_bc=False)     # b = 0: PETSc converges at iteration 0, x = 0
+    assert info["its"] == 0 and info["reason"] == 3
+    assert np.all(s.get_solution() == 0.0)
+    s.free()
+
+
+@pytest.mark.parametrize("n", [100])
+def test_generated_tria_and_tet(gpu, n):
+    """Mid-size generated meshes (tria100x100, tet 20^3): oracle finishes in seconds."""
+    m = M.gen_tria_poisson(n)
+    num = D.number(m, S.POISSON_TRIA)
+    s = S.SolverB200(0)
+    info = D.run_rank(s, m, num, rtol=1e-10)
+    rp, col, val = s.get_csr()
+    orp, ocol, oval, orhs = _oracle_system(m, S.POISSON_TRIA, num)
+    assert col.size == 67817                                   # explicit zeros kept (SURVEY.md 8d pattern trap)
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(val, oval)
+    ox, oits, _, _ = O.cg_jacobi(orp, ocol, oval, orhs, rtol=1e-10)
+    assert abs(info["its"] - oits) <= max(1, ITS_TOL * oits)
+    s.free()
+    m = M.gen_tetra(-1, 1, 20, -1, 1, 20, -1, 1, 20)
+    num = D.number(m, S.POISSON_TETRA)
+    s = S.SolverB200(0)
+    info = D.run_rank(s, m, num, rtol=1e-10)
+    rp, col, val = s.get_csr()
+    orp, ocol, oval, orhs = _oracle_system(m, S.POISSON_TETRA, num)
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(val, oval)
+    assert np.array_equal(s.get_rhs(), orhs)
+    ox, oits, _, _ = O.cg_jacobi(orp, ocol, oval, orhs, rtol=1e-10)
+    assert abs(info["its"] - oits) <= max(1, ITS_TOL * oits)
+    u = D.nodal_solution(num, s.get_solution())[0]
+    assert np.abs(u - (m.coords ** 2).sum(0)).max() < 1e-6
+    s.free()
