@@ -1,0 +1,33 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped on the single-GPU tier)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    from pfemfort_b200 import solver
+    return solver.device_count()
+
+
+@pytest.mark.parametrize("mesh,nproc,port", [("tet10", 2, 29621), ("beam3Dtet6366", 2, 29622), ("cookmembranetria32", 2, 29623),
+                                             ("gen_tet24", 2, 29624), ("gen_tet24", 4, 29625), ("gen_tet24", 8, 29626)])
+def test_multi_gpu_matches_oracle(gpu, tmp_path, mesh, nproc, port):
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    out = os.path.join(str(tmp_path), "result.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), "--mode", "gpu", "--mesh", mesh, "--out", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert res["pattern_bit_identical"] and res["values_bit_identical"] and res["rhs_bit_identical"]
+    assert all(x == res["oracle_reason"] == 2 for x in res["reason"])
+    assert len(set(res["its"])) == 1
+    assert abs(res["its"][0] - res["oracle_its"]) <= max(1, 0.02 * res["oracle_its"])
+    assert res["solution_rel_err"] < 1e-7
