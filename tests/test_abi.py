@@ -1,0 +1,55 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/pfem_b200.h declares; compute entry
+points fail loudly (PFEM_ERR_CUDA) without a GPU instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pfemfort_b200 import solver as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "pfem_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfem_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = S.load_library()
+    names = _declared()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pfem_b200.h but not exported"
+
+
+def test_host_side_exports():
+    lib = S.load_library()
+    for n in ("pfem_host_partition_mesh", "pfem_host_number_dofs", "pfem_host_renumber_conn", "pfem_host_elem_dof_array",
+              "pfem_host_select_elements", "pfem_host_gather_rows"):
+        assert hasattr(lib, n)
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    if S.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(S.PfemError) as ei:
+        S.SolverB200(0)
+    assert ei.value.status == S.ERR_CUDA
+    with pytest.raises(S.PfemError) as ei:
+        S.element_ke(S.POISSON_TRIA, [0, 1, 0], [0, 0, 1], None, [1, 1], [0, 1, 0])
+    assert ei.value.status == S.ERR_CUDA
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    import subprocess
+    out = subprocess.run(["ldd", S.LIBPATH], capture_output=True, text=True).stdout
+    assert "liborc" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "pfemfort_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "pyoracle" not in src and "liborc" not in src and "orc_" not in src, f

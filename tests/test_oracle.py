@@ -1,0 +1,162 @@
+"""CPU tests of the oracle (the checker): known answers of the reference's own fixtures, the independent
+closed-form Ke, and the identities of SURVEY.md section 8(c).  PARITY UNPINNED by golden vectors (the reference
+ships none); these are the pins that exist."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from pfemfort_b200 import driver as D, mesh as M, solver as S
+
+ED = D.DEFAULT_ELEMDATA
+TD = D.DEFAULT_TIMEDATA
+
+
+def _system(m, kind, fbc=True, fix=False):
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    o = O.number_dofs(m.nNode, ndof, m.dbc_node, m.dbc_dof, m.dbc_val)
+    conn_new = o["node_map_get_new"][m.conn - 1]
+    edof = O.elem_dof_array(conn_new, o["NodeDofArrayNew"])
+    rp, col = O.pattern(edof, o["size_global"])
+    val, rhs, nbad = O.assemble(kind, conn_new, m.coords, o["node_map_get_old"], edof, o["solnApplied"], ED[kind], TD, rp, col)
+    if fbc and m.fbc_node.size:
+        O.add_force_bc(rhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, o["node_map_get_new"], o["NodeDofArrayNew"], o["size_global"], fix=fix)
+    return o, edof, rp, col, val, rhs, nbad
+
+
+def _diag_sum(rp, col, val):
+    rows = np.repeat(np.arange(rp.size - 1), np.diff(rp))
+    return val[col == rows].sum()
+
+
+def test_single_precision_literals():
+    # w = REAL(1.0/6.0) = 0.1666666716337204 (elementutilitiespoisson.F:142): unit tet volume Jac = 1
+    x, y, z = [1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 0, 1.0]
+    K, F, rc = O.element_ke(O.POISSON_TETRA, x, y, z, [1, 1, 1], TD)
+    assert rc == 0
+    assert F[0] == 0.25 * 0.1666666716337204 * -6.0
+    assert K[0, 0] == 0.1666666716337204          # grad N1 = (1,0,0), dvol = w
+
+
+def test_tria20x20_known_answers(input_dir):
+    m = M.read_mesh(os.path.join(input_dir, "tria20x20"))
+    o, edof, rp, col, val, rhs, nbad = _system(m, O.POISSON_TRIA)
+    assert (o["size_global"], col.size, nbad) == (361, 2377, 0)
+    assert np.linalg.norm(rhs) == pytest.approx(3.162277655753922, rel=1e-13)
+    assert _diag_sum(rp, col, val) == pytest.approx(1444.0, rel=1e-13)
+    for rtol, its_expected in ((1e-5, 26), (1e-10, 31)):
+        x, its, reason, _ = O.cg_jacobi(rp, col, val, rhs, rtol=rtol)
+        assert (its, reason) == (its_expected, 2)
+    free = o["NodeDofArrayNew"][0] > 0
+    exact = M.exact_poisson_tria(m.coords[0, free], m.coords[1, free])
+    assert np.abs(x - exact).max() == pytest.approx(7.1146e-4, rel=1e-3)
+
+
+def test_tet10_known_answers(input_dir):
+    m = M.read_mesh(os.path.join(input_dir, "tet10"))
+    o, edof, rp, col, val, rhs, nbad = _system(m, O.POISSON_TETRA)
+    assert (o["size_global"], col.size, nbad) == (729, 9097, 0)
+    assert np.linalg.norm(rhs) == pytest.approx(24.573880283096567, rel=1e-13)
+    assert _diag_sum(rp, col, val) == pytest.approx(1506.6000449001795, rel=1e-13)   # needs w = 0.1666666716337204
+    for rtol, its_expected in ((1e-5, 28), (1e-10, 51)):
+        x, its, reason, _ = O.cg_jacobi(rp, col, val, rhs, rtol=rtol)
+        assert (its, reason) == (its_expected, 2)
+    free = o["NodeDofArrayNew"][0] > 0
+    assert np.abs(x - (m.coords[:, free] ** 2).sum(0)).max() == pytest.approx(1.157e-7, rel=1e-2)
+
+
+def test_beam3Dtet6366_documented_intent(input_dir):
+    raw = M.read_mesh(os.path.join(input_dir, "beam3Dtet6366"))
+    *_, nbad = _system(raw, O.ELASTICITY_TETRA)
+    assert nbad == raw.nElem == 7776                      # as shipped: every Jacobian negative (the reference STOPs)
+    m = M.read_mesh(os.path.join(input_dir, "beam3Dtet6366"), swap_34=True)
+    o, edof, rp, col, val, rhs, nbad = _system(m, O.ELASTICITY_TETRA, fbc=False)
+    assert (o["size_global"], col.size, nbad) == (5292, 200106, 0)
+    assert _diag_sum(rp, col, val) == pytest.approx(722620.29174, rel=1e-10)
+    assert np.linalg.norm(rhs) == pytest.approx(0.0151252780473, rel=1e-10)     # body force only
+    o, edof, rp, col, val, rhs, _ = _system(m, O.ELASTICITY_TETRA, fbc=True)
+    assert np.linalg.norm(rhs) == pytest.approx(1.73225048334, rel=1e-10)       # ForceBC via the reference's row formula
+    x, its, reason, _ = O.cg_jacobi(rp, col, val, rhs, rtol=1e-10)
+    assert reason == 2 and its == pytest.approx(661, abs=3)
+    u = np.zeros((3, m.nNode))
+    nda = o["NodeDofArrayNew"]
+    for d in range(3):
+        u[d, nda[d] > 0] = x[nda[d][nda[d] > 0] - 1]
+    assert np.sqrt((u ** 2).sum(0)).max() == pytest.approx(0.7078, abs=2e-4)
+
+
+def test_cookmembrane_documented_intent(input_dir):
+    m = M.read_mesh(os.path.join(input_dir, "cookmembranetria32"))
+    o, edof, rp, col, val, rhs, nbad = _system(m, O.ELASTICITY_TRIA)
+    assert (o["size_global"], col.size, nbad) == (2112, 28536, 0)
+    assert _diag_sum(rp, col, val) == pytest.approx(3372223.35481, rel=1e-10)
+    assert np.linalg.norm(rhs) == pytest.approx(17.5390190005, rel=1e-10)
+    x, its, reason, _ = O.cg_jacobi(rp, col, val, rhs, rtol=1e-10)
+    assert reason == 2 and its == pytest.approx(676, abs=3)
+    # zero right-hand side: PETSc converges at iteration 0 with x = 0 (never divides by p.w = 0)
+    x0, its0, reason0, _ = O.cg_jacobi(rp, col, val, np.zeros_like(rhs))
+    assert (its0, reason0) == (0, 3) and np.all(x0 == 0)
+
+
+def test_closed_form_tria_ke_cross_check():
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        x = np.array([0.0, 1.0, 0.0]) + 0.3 * rng.standard_normal(3)
+        y = np.array([0.0, 0.0, 1.0]) + 0.3 * rng.standard_normal(3)
+        K, F, rc = O.element_ke(O.POISSON_TRIA, x, y, None, [1, 1], TD)
+        if rc:
+            continue
+        Kc = O.tria_ke_closed_form(x, y)                  # triapoissonserialimpl1.F:580-594
+        assert np.allclose(K, Kc, rtol=1e-12, atol=1e-14)
+        assert np.abs(K.sum(1)).max() < 1e-13 and np.all(F == 0)
+
+
+def test_identities(input_dir):
+    m = M.read_mesh(os.path.join(input_dir, "tet10"))
+    vol = 0.0
+    for e in range(m.nElem):
+        n = m.conn[:, e] - 1
+        K, F, rc = O.element_ke(O.POISSON_TETRA, m.coords[0, n], m.coords[1, n], m.coords[2, n], [1, 1, 1], TD)
+        assert rc == 0 and np.abs(K.sum(1)).max() < 1e-12            # row sums of the Poisson Ke vanish
+        vol += F.sum() / -6.0                                          # sum Fe = force * volume
+    assert vol == pytest.approx(16.0 * 0.1666666716337204 * 6, rel=1e-12)   # domain volume 16 (w is the float 1/6)
+
+
+def test_explicit_zeros_are_part_of_the_pattern():
+    m = M.gen_tria_poisson(100)
+    o, edof, rp, col, val, rhs, _ = _system(m, O.POISSON_TRIA)
+    assert col.size == 67817                               # a value-pruning library would give 48609
+    assert (val == 0).sum() > 15000
+    for r in range(0, rp.size - 1, 97):
+        c = col[rp[r]:rp[r + 1]]
+        assert np.all(np.diff(c) > 0)                      # sorted unique columns
+
+
+def test_generators_reproduce_the_bundled_fixtures(input_dir):
+    t = M.read_mesh(os.path.join(input_dir, "tet10"))
+    g = M.gen_tetra(-2, 2, 10, -1, 1, 10, -1, 1, 10)
+    assert np.array_equal(g.coords, t.coords) and np.array_equal(g.conn, t.conn)
+    assert np.array_equal(g.dbc_node, t.dbc_node) and np.array_equal(g.dbc_val, t.dbc_val)
+    t = M.read_mesh(os.path.join(input_dir, "tria20x20"))
+    g = M.gen_tria_poisson(20)
+    assert np.array_equal(g.coords, t.coords) and np.array_equal(g.conn, t.conn)
+    assert np.array_equal(g.dbc_node, t.dbc_node) and np.array_equal(g.dbc_val, t.dbc_val)
+    b = M.read_mesh(os.path.join(input_dir, "beam3Dtet6366"), swap_34=True)
+    g = M.gen_tetra(-0.5, 0.5, 6, 0.0, 6.0, 36, -0.5, 0.5, 6, dbc="clamp_y0", ndof=3)
+    assert np.array_equal(g.conn, b.conn)                 # file ordering with 3<->4 swapped == genTetra ordering
+    assert np.abs(g.coords - b.coords).max() < 1e-8
+    assert np.array_equal(g.dbc_node, b.dbc_node) and np.array_equal(g.dbc_dof, b.dbc_dof)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/input/tet100-DirichBC.dat.gz"), reason="reference tree not present")
+def test_generators_against_the_large_reference_files():
+    import gzip
+    ref = np.loadtxt(gzip.open("/root/reference/input/tet100-DirichBC.dat.gz", "rt"))
+    g = M.gen_tetra(-1, 1, 100, -1, 1, 100, -1, 1, 100)
+    assert np.array_equal(g.dbc_node, ref[:, 0].astype(np.int32)) and np.array_equal(g.dbc_val, ref[:, 2])
+    ref = np.loadtxt(gzip.open("/root/reference/input/tria1000x1000-DirichBC.dat.gz", "rt"))
+    g = M.gen_tria_poisson(1000)
+    assert np.array_equal(g.dbc_node, ref[:, 0].astype(np.int32)) and np.array_equal(g.dbc_val, ref[:, 2])
+    nodes = np.loadtxt(gzip.open("/root/reference/input/tria1000x1000-nodes.dat.gz", "rt"))
+    assert np.array_equal(g.coords, nodes[:, 1:].T)
