@@ -27,6 +27,10 @@ struct AsmArgs {
     int *neg_count;
     int load_val, load_rhs;
     int max_seg_nnz;     // smem carve-up
+    const long long *ainc_off;
+    const int *ainc;
+    const int *conn4;
+    int *neg_flag;
 };
 
 template <int NPE, int NDIM>
@@ -137,6 +141,135 @@ __global__ void __launch_bounds__(R) assemble_kernel(const AsmArgs a)
     for (int k = threadIdx.x; k < nnz1 - nnz0; k += R) a.val[nnz0 + k] = acc[k];
 }
 
+// 256-bit read-only load of one node's (x, y, z, pad)
+__device__ __forceinline__ void ld_xyz(const double *p, double &x, double &y, double &z)
+{
+    double w;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+}
+
+// Streamed row-gather value pass.  Same arithmetic and summation order as assemble_kernel, but every input is a
+// coalesced stream: a warp owns a 32-row slice and reads its incidence entries column-major ({code, slot bytes},
+// slots precomputed at pattern time: no search), the element record is one int4 of node ids, coordinates are 256-bit
+// loads, and only the FP64 accumulators of the CTA's contiguous CSR segment live in shared memory.
+template <int KIND, int R>
+__global__ void __launch_bounds__(R) assemble_sell_kernel(const AsmArgs a)
+{
+    using T = ElemTraits<KIND>;
+    constexpr int NPE = T::NPE, NDOF = T::NDOF, NDIM = T::NDIM, NSIZE = NPE * NDOF;
+    constexpr int WORDS = NSIZE <= 4 ? 2 : 4;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *acc = reinterpret_cast<double *>(smem_raw);
+
+    const int r0 = blockIdx.x * R;
+    const int rend = min(r0 + R, a.nloc);
+    const int nnz0 = a.rowptr[r0], nnz1 = a.rowptr[rend];
+    for (int k = threadIdx.x; k < nnz1 - nnz0; k += R) acc[k] = a.load_val ? a.val[nnz0 + k] : 0.0;
+    __syncthreads();
+
+    const int r = r0 + threadIdx.x;
+    const int slice = r >> 5, lane = threadIdx.x & 31;
+    if (slice * 32 < a.nloc) {
+        Params<KIND> prm;
+        prm.init(a.elemData, a.timeData);
+        const bool live = r < rend;
+        double *racc = acc + (live ? a.rowptr[r] - nnz0 : 0);
+        double facc = (live && a.load_rhs) ? a.rhs[r] : 0.0;
+        const double du0[3] = {0.0, 0.0, 0.0};    // valC = 0 in the drivers (tetrapoissonparallelimpl1.F:824)
+        const long long o0 = a.ainc_off[slice];
+        const int width = (int)((a.ainc_off[slice + 1] - o0) >> 5);
+        const int *ip = a.ainc + (size_t)(o0 + lane) * WORDS;
+        for (int m = 0; m < width; m++, ip += 32 * WORDS) {
+            int code;
+            unsigned int sw[3];
+            if (WORDS == 2) {
+                const int2 v = __ldcs(reinterpret_cast<const int2 *>(ip));
+                code = v.x; sw[0] = (unsigned int)v.y; sw[1] = sw[2] = 0xFFFFFFFFu;
+            } else {
+                const int4 v = __ldcs(reinterpret_cast<const int4 *>(ip));
+                code = v.x; sw[0] = (unsigned int)v.y; sw[1] = (unsigned int)v.z; sw[2] = (unsigned int)v.w;
+            }
+            if (code < 0) continue;                        // slice padding
+            const int e = code / NSIZE, k = code - e * NSIZE;
+            const int4 cn = __ldg(reinterpret_cast<const int4 *>(a.conn4) + e);
+            const int nodes[4] = {cn.x, cn.y, cn.z, cn.w};
+            double x[NPE], y[NPE], z[NPE];
+#pragma unroll
+            for (int i = 0; i < NPE; i++) {
+                if (NDIM == 3) ld_xyz(a.xyz + (size_t)nodes[i] * 4, x[i], y[i], z[i]);
+                else {
+                    const double2 c = __ldg(reinterpret_cast<const double2 *>(a.xyz + (size_t)nodes[i] * 2));
+                    x[i] = c.x; y[i] = c.y; z[i] = 0.0;
+                }
+            }
+            ElemOp<KIND> op;
+            op.load_geom(x, y, z);
+            if (op.g.Jac < 0.0) { atomicOr(a.neg_flag, 1); continue; }   // the reference STOPs here
+            op.set_dvol(prm);
+            // MatSetValues(ADD): entry (row k, col j) += Klocal(j, k)
+            op.col_setup(prm, k);
+            bool any_dbc = false;
+#pragma unroll
+            for (int j = 0; j < NSIZE; j++) {
+                const unsigned int sl = (sw[j >> 2] >> (8 * (j & 3))) & 255u;
+                if (sl == 255u) { any_dbc = true; continue; }   // Dirichlet column: dropped by MatSetValues
+                racc[sl] = racc[sl] + op.K(prm, j);
+            }
+            // Flocal(k), then lifting in ascending Dirichlet local index: F_k -= Klocal(k, ii) * g_ii
+            double f = op.F(prm, k, du0);
+            if (any_dbc) {
+#pragma unroll
+                for (int ii = 0; ii < NSIZE; ii++) {
+                    const unsigned int sl = (sw[ii >> 2] >> (8 * (ii & 3))) & 255u;
+                    if (sl != 255u) continue;
+                    const double gval = a.applied[(size_t)nodes[ii / NDOF] * NDOF + (ii % NDOF)];
+                    op.col_setup(prm, ii);
+                    f = f - op.K(prm, k) * gval;
+                }
+            }
+            facc = facc + f;      // VecSetValues(ADD)
+        }
+        if (live) a.rhs[r] = facc;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nnz1 - nnz0; k += R) a.val[nnz0 + k] = acc[k];
+}
+
+// error path only: number of elements with Jac < 0 among those that touch an owned row
+template <int KIND>
+__global__ void count_negative_kernel(int nElem, int rec_ints, const int *__restrict__ erec, const double *__restrict__ xyz,
+                                      int row_lo, int row_hi, int *__restrict__ count)
+{
+    using T = ElemTraits<KIND>;
+    constexpr int NPE = T::NPE, NDIM = T::NDIM, NSIZE = T::NPE * T::NDOF;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElem; e += gridDim.x * blockDim.x) {
+        const int *rec = erec + (size_t)e * rec_ints;
+        bool owned = false;
+        for (int q = 0; q < NSIZE; q++) owned |= rec[NPE + q] >= row_lo && rec[NPE + q] < row_hi;
+        if (!owned) continue;
+        int nodes[NPE];
+        for (int i = 0; i < NPE; i++) nodes[i] = rec[i];
+        double x[NPE], y[NPE], z[NPE];
+        load_coords<NPE, NDIM>(xyz, nodes, x, y, z);
+        ElemOp<KIND> op;
+        op.load_geom(x, y, z);
+        if (op.g.Jac < 0.0) atomicAdd(count, 1);
+    }
+}
+
+template <int KIND, int R>
+static int launch_assemble_sell(pfem_solver *h, const AsmArgs &args)
+{
+    const int blocks = ceil_div(h->size_local, R);
+    if (blocks == 0) return PFEM_OK;
+    PFEM_CUDA(cudaFuncSetAttribute(assemble_sell_kernel<KIND, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->asm_smem));
+    assemble_sell_kernel<KIND, R><<<blocks, R, h->asm_smem, h->stream>>>(args);
+    h->launches++;
+    PFEM_CUDA(cudaGetLastError());
+    return PFEM_OK;
+}
+
 template <int KIND, int R>
 static int launch_assemble(pfem_solver *h, const AsmArgs &args)
 {
@@ -152,6 +285,14 @@ static int launch_assemble(pfem_solver *h, const AsmArgs &args)
 template <int KIND>
 static int dispatch_rows(pfem_solver *h, const AsmArgs &args)
 {
+    if (h->asm_sell) {
+        switch (h->asm_rows_per_cta) {
+        case 256: return launch_assemble_sell<KIND, 256>(h, args);
+        case 128: return launch_assemble_sell<KIND, 128>(h, args);
+        case 64: return launch_assemble_sell<KIND, 64>(h, args);
+        case 32: return launch_assemble_sell<KIND, 32>(h, args);
+        }
+    }
     switch (h->asm_rows_per_cta) {
     case 256: return launch_assemble<KIND, 256>(h, args);
     case 128: return launch_assemble<KIND, 128>(h, args);
@@ -183,7 +324,7 @@ int plan_assembly(pfem_solver *h)
                 mi = std::max(mi, ip[r1] - ip[r0]);
             }
             mn = (mn + 1) & ~1;   // keep the int arrays 8-byte aligned
-            const size_t bytes = (size_t)mn * 12 + (size_t)mi * 4 + 16;
+            const size_t bytes = h->asm_sell ? (size_t)mn * 8 + 16 : (size_t)mn * 12 + (size_t)mi * 4 + 16;
             if (bytes <= limit) {
                 h->asm_rows_per_cta = R;
                 h->asm_smem = bytes;
@@ -218,6 +359,7 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     a.elemData = dED.p; a.timeData = dTD.p; a.neg_count = h->neg_count.p;
     a.load_val = h->values_zero ? 0 : 1; a.load_rhs = h->rhs_zero ? 0 : 1;
     a.max_seg_nnz = h->asm_max_seg;
+    a.ainc_off = h->ainc_off.p; a.ainc = h->ainc.p; a.conn4 = h->conn4.p; a.neg_flag = h->neg_count.p;
     PFEM_CUDA(cudaEventRecord(h->ev0, s));
     int st = PFEM_OK;
     switch (h->kind) {
@@ -232,6 +374,19 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     int neg = 0;
     PFEM_CUDA(cudaMemcpyAsync(&neg, h->neg_count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PFEM_CUDA(cudaStreamSynchronize(s));
+    if (neg && h->asm_sell) {      // the streamed kernel only raises a flag: count the offending elements now
+        PFEM_CUDA(cudaMemsetAsync(h->neg_count.p, 0, sizeof(int), s));
+        const int G = h->sm_count * 8;
+        switch (h->kind) {
+        case PFEM_POISSON_TRIA: count_negative_kernel<POISSON_TRIA><<<G, 256, 0, s>>>(h->nElem, h->rec_ints, h->erec.p, h->xyz.p, h->row_lo, h->row_hi, h->neg_count.p); break;
+        case PFEM_POISSON_TETRA: count_negative_kernel<POISSON_TETRA><<<G, 256, 0, s>>>(h->nElem, h->rec_ints, h->erec.p, h->xyz.p, h->row_lo, h->row_hi, h->neg_count.p); break;
+        case PFEM_ELASTICITY_TRIA: count_negative_kernel<ELASTICITY_TRIA><<<G, 256, 0, s>>>(h->nElem, h->rec_ints, h->erec.p, h->xyz.p, h->row_lo, h->row_hi, h->neg_count.p); break;
+        default: count_negative_kernel<ELASTICITY_TETRA><<<G, 256, 0, s>>>(h->nElem, h->rec_ints, h->erec.p, h->xyz.p, h->row_lo, h->row_hi, h->neg_count.p); break;
+        }
+        h->launches++;
+        PFEM_CUDA(cudaMemcpyAsync(&neg, h->neg_count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+    }
     float ms = 0.f;
     PFEM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->t_assemble = ms * 1e-3;

@@ -107,6 +107,13 @@ struct pfem_solver {
     pfem::DevBuf<int> rowptr, col;
     pfem::DevBuf<double> val, rhs;
     pfem::DevBuf<int> rinc_ptr, rinc;      // row -> (e*nsize + k) incidences, ascending
+    // value-pass streams: per 32-row slice, column-major incidence entries {code, slot bytes} (warp-coalesced),
+    // and a conn-only int4 record per element
+    pfem::DevBuf<long long> ainc_off;      // [nslices+1] entry offsets
+    pfem::DevBuf<int> ainc;                // entries of ainc_words ints: code (or -1 = padding), then nsize slot bytes
+    pfem::DevBuf<int> conn4;               // [nElem][4] 0-based NEW node ids
+    int ainc_words = 0;
+    bool asm_sell = false;                 // false: rows wider than 254 entries -> generic (binary search) kernel
     bool values_zero = true, rhs_zero = true;
     int asm_rows_per_cta = 0, asm_max_seg = 0;
     size_t asm_smem = 0;

@@ -7,6 +7,8 @@
 // Also builds the row -> element incidence lists (ascending element id) that the value pass gathers from.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+
 #include "internal.cuh"
 
 namespace pfem {
@@ -216,6 +218,117 @@ __global__ void compact_cols_kernel(int nloc, const long long *__restrict__ cand
     }
 }
 
+// ---- value-pass streams ------------------------------------------------------------------------------------------
+
+__global__ void conn4_kernel(int nElem, int npe, int rec_ints, const int *__restrict__ erec, int *__restrict__ conn4)
+{
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElem; e += gridDim.x * blockDim.x) {
+        int4 v;
+        const int *r = erec + (size_t)e * rec_ints;
+        v.x = r[0]; v.y = r[1]; v.z = r[2]; v.w = npe == 4 ? r[3] : r[2];
+        reinterpret_cast<int4 *>(conn4)[e] = v;
+    }
+}
+
+// one warp per 32-row slice: padded incidence count of the slice (in entries)
+__global__ void inc_width_kernel(int nloc, int nslices, const int *__restrict__ rinc_ptr, const int *__restrict__ rowptr,
+                                 long long *__restrict__ slice_sz, int *__restrict__ wide_flag)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nslices; s += warps) {
+        const int r = s * 32 + lane;
+        int w = r < nloc ? rinc_ptr[r + 1] - rinc_ptr[r] : 0;
+        if (r < nloc && rowptr[r + 1] - rowptr[r] > 254) atomicOr(wide_flag, 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+        if (lane == 0) slice_sz[s] = (long long)w * 32;
+    }
+}
+
+// entry = { code = e*nsize+k, slot bytes: position of dof j of element e inside the row's sorted column list, 255 = Dirichlet }
+__global__ void fill_asm_inc_kernel(int nloc, int nrows_padded, int nsize, int npe, int rec_ints, int words,
+                                    const int *__restrict__ erec, const int *__restrict__ rinc_ptr,
+                                    const int *__restrict__ rinc, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                    const long long *__restrict__ inc_off, int *__restrict__ ainc)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows_padded; r += gridDim.x * blockDim.x) {
+        const int s = r >> 5, lane = r & 31;
+        const long long base = inc_off[s] + lane;
+        const int width = (int)((inc_off[s + 1] - inc_off[s]) >> 5);
+        int m = 0;
+        if (r < nloc) {
+            const int c0 = rowptr[r], len = rowptr[r + 1] - c0;
+            for (int q = rinc_ptr[r]; q < rinc_ptr[r + 1]; q++, m++) {
+                const int code = rinc[q];
+                const int e = code / nsize;
+                const int *dof = erec + (size_t)e * rec_ints + npe;
+                unsigned int w[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+                for (int j = 0; j < nsize; j++) {
+                    const int c = dof[j];
+                    if (c < 0) continue;
+                    int lo = 0, hi = len;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (col[c0 + mid] < c) lo = mid + 1; else hi = mid;
+                    }
+                    const unsigned int sh = 8u * (j & 3);
+                    w[j >> 2] = (w[j >> 2] & ~(0xFFu << sh)) | ((unsigned int)(lo & 255) << sh);
+                }
+                int *out = ainc + (size_t)(base + (long long)m * 32) * words;
+                out[0] = code;
+                for (int q2 = 1; q2 < words; q2++) out[q2] = (int)w[q2 - 1];
+            }
+        }
+        for (; m < width; m++) {
+            int *out = ainc + (size_t)(base + (long long)m * 32) * words;
+            out[0] = -1;
+            for (int q2 = 1; q2 < words; q2++) out[q2] = -1;
+        }
+    }
+}
+
+static int build_asm_streams(pfem_solver *h)
+{
+    cudaStream_t s = h->stream;
+    const int G = h->sm_count * 8, nloc = h->size_local;
+    const int nslices = (nloc + 31) / 32;
+    h->asm_sell = false;
+    h->ainc_words = h->nsize <= 4 ? 2 : 4;
+    DevBuf<long long> sz;
+    DevBuf<int> wide;
+    PFEM_TRY(sz.alloc((size_t)nslices + 1));
+    PFEM_TRY(wide.alloc(1));
+    PFEM_CUDA(cudaMemsetAsync(sz.p, 0, ((size_t)nslices + 1) * sizeof(long long), s));
+    PFEM_CUDA(cudaMemsetAsync(wide.p, 0, sizeof(int), s));
+    inc_width_kernel<<<G, 256, 0, s>>>(nloc, nslices, h->rinc_ptr.p, h->rowptr.p, sz.p, wide.p);
+    h->launches++;
+    PFEM_TRY(h->ainc_off.alloc((size_t)nslices + 1));
+    size_t bytes = 0;
+    PFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, sz.p, h->ainc_off.p, nslices + 1, s));
+    DevBuf<char> tmp;
+    PFEM_TRY(tmp.alloc(bytes));
+    PFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, sz.p, h->ainc_off.p, nslices + 1, s));
+    h->launches++;
+    long long nent = 0;
+    int iswide = 0;
+    PFEM_CUDA(cudaMemcpyAsync(&nent, h->ainc_off.p + nslices, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaMemcpyAsync(&iswide, wide.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    const char *force = getenv("PFEM_FORCE_GENERIC_ASM");                 // test hook: exercise the generic kernel
+    if (iswide || nent * h->ainc_words >= (1LL << 31) || (force && force[0] == '1')) return PFEM_OK;   // generic kernel handles it
+    PFEM_TRY(h->ainc.alloc((size_t)nent * h->ainc_words));
+    PFEM_TRY(h->conn4.alloc((size_t)h->nElem * 4));
+    conn4_kernel<<<G, 256, 0, s>>>(h->nElem, h->npe, h->rec_ints, h->erec.p, h->conn4.p);
+    fill_asm_inc_kernel<<<G, 128, 0, s>>>(nloc, nslices * 32, h->nsize, h->npe, h->rec_ints, h->ainc_words, h->erec.p,
+                                          h->rinc_ptr.p, h->rinc.p, h->rowptr.p, h->col.p, h->ainc_off.p, h->ainc.p);
+    h->launches += 2;
+    PFEM_CUDA(cudaGetLastError());
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    h->asm_sell = true;
+    return PFEM_OK;
+}
+
 int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
 {
     if (!h->initialised) { set_error("pfem_solver_set_pattern: call pfem_solver_initialise first"); return PFEM_ERR_STATE; }
@@ -324,6 +437,7 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
     h->values_zero = true;
     h->rhs_zero = true;
     PFEM_TRY(h->neg_count.alloc(1));
+    PFEM_TRY(build_asm_streams(h));
     h->asm_rows_per_cta = 0;
     PFEM_TRY(plan_assembly(h));
     return PFEM_OK;

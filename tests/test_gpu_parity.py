@@ -236,3 +236,18 @@ def test_generated_tria_and_tet(gpu, n):
     u = D.nodal_solution(num, s.get_solution())[0]
     assert np.abs(u - (m.coords ** 2).sum(0)).max() < 1e-6
     s.free()
+
+
+def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch):
+    """Rows wider than 254 entries fall back to the binary-search kernel; force it and compare bit for bit."""
+    for name in ("tet10", "beam3Dtet6366"):
+        m, kind = _load(name, input_dir)
+        num = D.number(m, kind)
+        out = []
+        for force in ("0", "1"):
+            monkeypatch.setenv("PFEM_FORCE_GENERIC_ASM", force)
+            s = S.SolverB200(0)
+            D.run_rank(s, m, num, do_solve=False)
+            out.append((s.get_csr()[2], s.get_rhs()))
+            s.free()
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
