@@ -261,12 +261,20 @@ def main():
 
     s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
 
+    stage_t = {}
+
+    def timed(name, fn, *a):
+        t = time.perf_counter()
+        r = fn(*a)
+        stage_t[name] = stage_t.get(name, 0.0) + time.perf_counter() - t
+        return r
+
     def upload_and_pattern():
         s.initialise(size_local, num.size_global)
         s.set_options(rtol=RTOL, max_it=100000, pc_type=S.PC_JACOBI)
-        s.set_mesh(kind, conn_p, coords_p, map_p)
-        s.set_pattern(edof_p)
-        s.set_applied(applied_p)
+        timed("set_mesh", s.set_mesh, kind, conn_p, coords_p, map_p)
+        timed("set_pattern", s.set_pattern, edof_p)
+        timed("set_applied", s.set_applied, applied_p)
 
     def hot_step():
         s.setZero()
@@ -331,9 +339,11 @@ def main():
         barrier()
         s.launch_count(reset=True)
         t0 = time.perf_counter()
+        if k == 1:
+            stage_t.clear()
         upload_and_pattern()
-        info = hot_step()
-        s.get_solution(xout_p)
+        info = timed("hot_step", hot_step)
+        timed("get_solution", s.get_solution, xout_p)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         if k > 0:
@@ -367,7 +377,8 @@ def main():
                      "launches_timed": int(spmv_n), "peak_source": peak_src, "scope": "rank 0 share"},
         "e2e": {"value": e2e_value, "unit": "DOF-iter/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": 1e3 * e2e_t / e2e_steps, "steps": e2e_steps,
-                "includes": "mesh upload, pattern pass, value pass, solve, solution read-back"},
+                "includes": "mesh upload, pattern pass, value pass, solve, solution read-back",
+                "stage_ms": {k_: 1e3 * v_ / e2e_steps for k_, v_ in stage_t.items()}},
         "gpu_launches": launches_total, "gpu_launches_e2e": launches_e2e,
         "setup_s": t_setup, "clocks": clocks,
     }

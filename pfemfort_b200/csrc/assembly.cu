@@ -10,6 +10,8 @@
 // segment, loaded and stored with coalesced accesses).  Per matrix entry the contributions are thus
 // summed in exactly the order of the reference's sequential np=1 run, so the result is deterministic and,
 // because the TU is built with -fmad=false, bit-identical to the no-FMA CPU evaluation.
+#include <cstdlib>
+
 #include "elements.cuh"
 #include "internal.cuh"
 
@@ -31,6 +33,7 @@ struct AsmArgs {
     const int *ainc;
     const int *conn4;
     int *neg_flag;
+    int unit;            // kx = ky = kz = af = 1.0 exactly
 };
 
 template <int NPE, int NDIM>
@@ -152,12 +155,17 @@ __device__ __forceinline__ void ld_xyz(const double *p, double &x, double &y, do
 // coalesced stream: a warp owns a 32-row slice and reads its incidence entries column-major ({code, slot bytes},
 // slots precomputed at pattern time: no search), the element record is one int4 of node ids, coordinates are 256-bit
 // loads, and only the FP64 accumulators of the CTA's contiguous CSR segment live in shared memory.
-template <int KIND, int R>
+// The loop is software-pipelined: incidence entries three iterations ahead, node ids two ahead, and the next
+// iteration's coordinates already in flight into registers while the current element is computed.
+// UNIT: kx = ky = kz = af = 1.0 exactly (the drivers' constants): multiplications by 1.0 are skipped (bit-identical).
+template <int KIND, int R, bool UNIT>
 __global__ void __launch_bounds__(R) assemble_sell_kernel(const AsmArgs a)
 {
     using T = ElemTraits<KIND>;
     constexpr int NPE = T::NPE, NDOF = T::NDOF, NDIM = T::NDIM, NSIZE = NPE * NDOF;
     constexpr int WORDS = NSIZE <= 4 ? 2 : 4;
+    constexpr int NW = (NSIZE + 3) / 4;          // slot words in use
+    constexpr int XYZ = NDIM == 3 ? 4 : 2;       // doubles per node record
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *acc = reinterpret_cast<double *>(smem_raw);
@@ -175,53 +183,82 @@ __global__ void __launch_bounds__(R) assemble_sell_kernel(const AsmArgs a)
         prm.init(a.elemData, a.timeData);
         const bool live = r < rend;
         double *racc = acc + (live ? a.rowptr[r] - nnz0 : 0);
+        double *dummy = acc + a.max_seg_nnz + threadIdx.x;      // sink for Dirichlet columns (never read)
         double facc = (live && a.load_rhs) ? a.rhs[r] : 0.0;
-        const double du0[3] = {0.0, 0.0, 0.0};    // valC = 0 in the drivers (tetrapoissonparallelimpl1.F:824)
         const long long o0 = a.ainc_off[slice];
         const int width = (int)((a.ainc_off[slice + 1] - o0) >> 5);
         const int *ip = a.ainc + (size_t)(o0 + lane) * WORDS;
-        for (int m = 0; m < width; m++, ip += 32 * WORDS) {
-            int code;
-            unsigned int sw[3];
-            if (WORDS == 2) {
-                const int2 v = __ldcs(reinterpret_cast<const int2 *>(ip));
-                code = v.x; sw[0] = (unsigned int)v.y; sw[1] = sw[2] = 0xFFFFFFFFu;
-            } else {
-                const int4 v = __ldcs(reinterpret_cast<const int4 *>(ip));
-                code = v.x; sw[0] = (unsigned int)v.y; sw[1] = (unsigned int)v.z; sw[2] = (unsigned int)v.w;
-            }
-            if (code < 0) continue;                        // slice padding
-            const int e = code / NSIZE, k = code - e * NSIZE;
-            const int4 cn = __ldg(reinterpret_cast<const int4 *>(a.conn4) + e);
-            const int nodes[4] = {cn.x, cn.y, cn.z, cn.w};
-            double x[NPE], y[NPE], z[NPE];
-#pragma unroll
-            for (int i = 0; i < NPE; i++) {
-                if (NDIM == 3) ld_xyz(a.xyz + (size_t)nodes[i] * 4, x[i], y[i], z[i]);
-                else {
-                    const double2 c = __ldg(reinterpret_cast<const double2 *>(a.xyz + (size_t)nodes[i] * 2));
-                    x[i] = c.x; y[i] = c.y; z[i] = 0.0;
+        const int4 *conn = reinterpret_cast<const int4 *>(a.conn4);
+
+        struct Ent { int code; unsigned int sw[3]; };
+        auto load_entry = [&](int m) {
+            Ent t;
+            t.code = -1; t.sw[0] = t.sw[1] = t.sw[2] = 0u;
+            if (m < width) {
+                const int *q = ip + (size_t)m * 32 * WORDS;
+                if (WORDS == 2) {
+                    const int2 v = __ldcs(reinterpret_cast<const int2 *>(q));
+                    t.code = v.x; t.sw[0] = (unsigned int)v.y;
+                } else {
+                    const int4 v = __ldcs(reinterpret_cast<const int4 *>(q));
+                    t.code = v.x; t.sw[0] = (unsigned int)v.y; t.sw[1] = (unsigned int)v.z; t.sw[2] = (unsigned int)v.w;
                 }
             }
+            return t;
+        };
+        auto load_conn = [&](const Ent &t) { return t.code >= 0 ? __ldg(conn + t.code / NSIZE) : make_int4(0, 0, 0, 0); };
+        auto load_xyz = [&](const int4 &c, double (&x)[NPE], double (&y)[NPE], double (&z)[NPE]) {
+            const int nd[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < NPE; i++) {
+                if (NDIM == 3) ld_xyz(a.xyz + (size_t)nd[i] * 4, x[i], y[i], z[i]);
+                else {
+                    const double2 t = __ldg(reinterpret_cast<const double2 *>(a.xyz + (size_t)nd[i] * 2));
+                    x[i] = t.x; y[i] = t.y; z[i] = 0.0;
+                }
+            }
+        };
+        Ent e0 = load_entry(0), e1 = load_entry(1), e2 = load_entry(2);
+        int4 c0 = load_conn(e0), c1 = load_conn(e1);
+        double xq[NPE], yq[NPE], zq[NPE];                  // coordinates of the element of the NEXT iteration
+        load_xyz(c0, xq, yq, zq);
+        for (int m = 0; m < width; m++) {
+            const Ent e3 = load_entry(m + 3);
+            const int4 c2 = load_conn(e2);
+            double x[NPE], y[NPE], z[NPE];
+#pragma unroll
+            for (int i = 0; i < NPE; i++) { x[i] = xq[i]; y[i] = yq[i]; z[i] = zq[i]; }
+            load_xyz(c1, xq, yq, zq);                      // in flight during this iteration's arithmetic
+            const Ent cur = e0;
+            const int4 cn = c0;
+            e0 = e1; e1 = e2; e2 = e3; c0 = c1; c1 = c2;
+            if (cur.code < 0) continue;                    // slice padding
+            const int k = cur.code % NSIZE;
+            const int nodes[4] = {cn.x, cn.y, cn.z, cn.w};
             ElemOp<KIND> op;
             op.load_geom(x, y, z);
             if (op.g.Jac < 0.0) { atomicOr(a.neg_flag, 1); continue; }   // the reference STOPs here
             op.set_dvol(prm);
-            // MatSetValues(ADD): entry (row k, col j) += Klocal(j, k)
-            op.col_setup(prm, k);
-            bool any_dbc = false;
+            // MatSetValues(ADD): entry (row k, col j) += Klocal(j, k); Dirichlet columns (slot byte 0xFF) are dropped
+            if (UNIT) op.col_setup_unit(k); else op.col_setup(prm, k);
 #pragma unroll
             for (int j = 0; j < NSIZE; j++) {
-                const unsigned int sl = (sw[j >> 2] >> (8 * (j & 3))) & 255u;
-                if (sl == 255u) { any_dbc = true; continue; }   // Dirichlet column: dropped by MatSetValues
-                racc[sl] = racc[sl] + op.K(prm, j);
+                const unsigned int sl = (cur.sw[j >> 2] >> (8 * (j & 3))) & 255u;
+                double *dst = sl == 255u ? dummy : racc + sl;
+                *dst = *dst + (UNIT ? op.K_unit(j) : op.K(prm, j));
             }
             // Flocal(k), then lifting in ascending Dirichlet local index: F_k -= Klocal(k, ii) * g_ii
-            double f = op.F(prm, k, du0);
+            double f = op.F0(prm, k);
+            bool any_dbc = false;
+#pragma unroll
+            for (int q = 0; q < NW; q++) {
+                const unsigned int v = ~cur.sw[q];         // a 0xFF slot byte becomes a zero byte (unused bytes hold 0x00)
+                any_dbc |= ((v - 0x01010101u) & ~v & 0x80808080u) != 0u;
+            }
             if (any_dbc) {
 #pragma unroll
                 for (int ii = 0; ii < NSIZE; ii++) {
-                    const unsigned int sl = (sw[ii >> 2] >> (8 * (ii & 3))) & 255u;
+                    const unsigned int sl = (cur.sw[ii >> 2] >> (8 * (ii & 3))) & 255u;
                     if (sl != 255u) continue;
                     const double gval = a.applied[(size_t)nodes[ii / NDOF] * NDOF + (ii % NDOF)];
                     op.col_setup(prm, ii);
@@ -263,8 +300,15 @@ static int launch_assemble_sell(pfem_solver *h, const AsmArgs &args)
 {
     const int blocks = ceil_div(h->size_local, R);
     if (blocks == 0) return PFEM_OK;
-    PFEM_CUDA(cudaFuncSetAttribute(assemble_sell_kernel<KIND, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->asm_smem));
-    assemble_sell_kernel<KIND, R><<<blocks, R, h->asm_smem, h->stream>>>(args);
+    constexpr bool POISSON = KIND == POISSON_TRIA || KIND == POISSON_TETRA;
+    const size_t smem = h->asm_smem;                                   // includes one sink accumulator per thread
+    if (POISSON && args.unit) {
+        PFEM_CUDA(cudaFuncSetAttribute(assemble_sell_kernel<KIND, R, POISSON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        assemble_sell_kernel<KIND, R, POISSON><<<blocks, R, smem, h->stream>>>(args);
+    } else {
+        PFEM_CUDA(cudaFuncSetAttribute(assemble_sell_kernel<KIND, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        assemble_sell_kernel<KIND, R, false><<<blocks, R, smem, h->stream>>>(args);
+    }
     h->launches++;
     PFEM_CUDA(cudaGetLastError());
     return PFEM_OK;
@@ -313,10 +357,15 @@ int plan_assembly(pfem_solver *h)
     int max_smem = 0;
     PFEM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     const int shapes[4] = {256, 128, 64, 32};
+    const char *env = getenv("PFEM_ASM_ROWS");            // tuning hook: force the rows-per-CTA shape
+    const int forced = env ? atoi(env) : 0;
     // prefer the largest shape that still lets two CTAs share an SM
     for (int pass = 0; pass < 2; pass++) {
         const size_t limit = pass == 0 ? (size_t)max_smem / 2 - 1024 : (size_t)max_smem;
-        for (int R : shapes) {
+        for (int idx = 0; idx < 4; idx++) {
+            // the streamed kernel is register-bound and barrier-free at one warp per CTA: prefer the smallest shape
+            const int R = h->asm_sell ? shapes[3 - idx] : shapes[idx];
+            if (forced && R != forced) continue;
             int mn = 0, mi = 0;
             for (int r0 = 0; r0 < nloc; r0 += R) {
                 const int r1 = r0 + R < nloc ? r0 + R : nloc;
@@ -324,7 +373,7 @@ int plan_assembly(pfem_solver *h)
                 mi = std::max(mi, ip[r1] - ip[r0]);
             }
             mn = (mn + 1) & ~1;   // keep the int arrays 8-byte aligned
-            const size_t bytes = h->asm_sell ? (size_t)mn * 8 + 16 : (size_t)mn * 12 + (size_t)mi * 4 + 16;
+            const size_t bytes = h->asm_sell ? (size_t)mn * 8 + 16 + (size_t)R * 8 : (size_t)mn * 12 + (size_t)mi * 4 + 16;
             if (bytes <= limit) {
                 h->asm_rows_per_cta = R;
                 h->asm_smem = bytes;
@@ -360,6 +409,7 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     a.load_val = h->values_zero ? 0 : 1; a.load_rhs = h->rhs_zero ? 0 : 1;
     a.max_seg_nnz = h->asm_max_seg;
     a.ainc_off = h->ainc_off.p; a.ainc = h->ainc.p; a.conn4 = h->conn4.p; a.neg_flag = h->neg_count.p;
+    a.unit = (td[1] == 1.0 && ed[0] == 1.0 && ed[1] == 1.0 && (h->kind == PFEM_POISSON_TRIA || ed[2] == 1.0)) ? 1 : 0;
     PFEM_CUDA(cudaEventRecord(h->ev0, s));
     int st = PFEM_OK;
     switch (h->kind) {

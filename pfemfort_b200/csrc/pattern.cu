@@ -263,10 +263,10 @@ __global__ void fill_asm_inc_kernel(int nloc, int nrows_padded, int nsize, int n
                 const int code = rinc[q];
                 const int e = code / nsize;
                 const int *dof = erec + (size_t)e * rec_ints + npe;
-                unsigned int w[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+                unsigned int w[3] = {0u, 0u, 0u};             // unused bytes 0x00, Dirichlet dofs 0xFF
                 for (int j = 0; j < nsize; j++) {
                     const int c = dof[j];
-                    if (c < 0) continue;
+                    if (c < 0) { w[j >> 2] |= 0xFFu << (8u * (j & 3)); continue; }
                     int lo = 0, hi = len;
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
