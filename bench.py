@@ -363,6 +363,7 @@ def main():
         "config": {"workload": f"genTetra {args.cells}^3 x6 P1-tet Poisson on [-1,1]^3, Jacobi-CG rtol {RTOL:g}",
                    "elements": int(m.nElem), "nodes": int(m.nNode), "dof": int(N), "nnz": nnz_total,
                    "partition": "none" if world == 1 else args.partition, "parallelism": f"rows{world}",
+                   "exchange": {0: "none", 1: "nccl", 2: "peer-memory kernels (NVLink)"}[s.comm_mode()],
                    "l2": "inputs larger than L2 (matrix >= 1.4 GB per pass vs 126 MB L2); no flush needed",
                    "timing": "CUDA events on the library stream (t_assemble, t_solve), max over ranks; ms_per_step = host wall between barriers"},
         "iterations_per_step": its_per_step, "reason": info["reason"], "max_nodal_error": err,

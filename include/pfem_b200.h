@@ -160,6 +160,8 @@ int pfem_solver_get_csr(pfem_solver_t *h, int *rowptr, int *col, double *val);
 int pfem_solver_get_info(pfem_solver_t *h, int *its, int *reason, double *rnorm, double *t_assemble_s,
                          double *t_solve_s);
 int pfem_solver_get_state(pfem_solver_t *h, int *state, int *row_start, int *row_end, int *size_global);
+/* exchange path in use for nranks > 1: 0 = single rank, 1 = NCCL send/recv + all-reduce, 2 = peer-memory kernels (NVLink, CUDA IPC) */
+int pfem_solver_comm_mode(pfem_solver_t *h, int *mode);
 /* kernel launches issued on this handle since the last call with reset != 0 */
 int pfem_solver_launch_count(pfem_solver_t *h, long long *launches, int reset);
 /* Run the CG SpMV (w = A p on an internal vector) `reps` times and report the mean device time per

@@ -144,6 +144,7 @@ int pfem_solver_free(pfem_solver_t *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    comm_p2p_teardown(h, true);
     comm_destroy(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->cg_host) cudaFreeHost(h->cg_host);
@@ -390,6 +391,13 @@ int pfem_solver_get_state(pfem_solver_t *h, int *state, int *row_start, int *row
     if (row_start) *row_start = h->row_lo;
     if (row_end) *row_end = h->row_hi;
     if (size_global) *size_global = h->size_global;
+    return PFEM_OK;
+}
+
+int pfem_solver_comm_mode(pfem_solver_t *h, int *mode)
+{
+    if (!h) { set_error("NULL handle"); return PFEM_ERR_ARG; }
+    if (mode) *mode = h->nranks == 1 ? 0 : (h->p2p ? 2 : 1);
     return PFEM_OK;
 }
 

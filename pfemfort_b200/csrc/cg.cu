@@ -66,6 +66,75 @@ __device__ __forceinline__ double reduce_partials(const double *partials, int n,
     return block_sum(s, sh);
 }
 
+
+// ---- peer-memory exchange primitives (NVLink, CUDA IPC mapped) ------------------------------------------------------
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.global.release.sys.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.relaxed.sys.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v)
+{
+    asm volatile("st.global.relaxed.sys.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long p2p_tag(const CgState *st, int kind)
+{
+    return (st->seq << 32) | (unsigned long long)(4u * (unsigned int)st->iter + (unsigned int)kind);
+}
+
+// spin until *flag == tag (bounded: a dead peer must not hang the GPU); returns false on time-out
+__device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long tag)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) != tag) {
+        if (clock64() - t0 > 20000000000LL) return false;     // ~10 s
+        __nanosleep(20);
+    }
+    return true;
+}
+
+// All-reduce (sum) of two doubles across the ranks through the peers' mailboxes, executed by the FIRST WARP of one CTA.
+// Every rank sums the P contributions in rank order, so all ranks obtain bit-identical results.
+__device__ __forceinline__ void p2p_allreduce2(const P2pCtx *c, CgState *st, int phase, unsigned long long tag, double &v0,
+                                               double &v1, double *sh)
+{
+    const int lane = threadIdx.x;      // caller guarantees threadIdx.x < 32
+    const int P = c->nranks, me = c->rank;
+    if (lane < P) {
+        P2pMail *dst = c->mail[lane];
+        st_relaxed_sys_f64(&dst->red_val[phase][me][0], v0);
+        st_relaxed_sys_f64(&dst->red_val[phase][me][1], v1);
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[phase][me], tag);
+    }
+    bool ok = true;
+    if (lane < P) {
+        const P2pMail *mine = c->mail[me];
+        ok = p2p_wait(&mine->red_flag[phase][lane], tag);
+        sh[2 * lane] = ld_volatile_f64(&mine->red_val[phase][lane][0]);
+        sh[2 * lane + 1] = ld_volatile_f64(&mine->red_val[phase][lane][1]);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    double s0 = 0.0, s1 = 0.0;
+    for (int q = 0; q < P; q++) { s0 += sh[2 * q]; s1 += sh[2 * q + 1]; }
+    v0 = s0; v1 = s1;
+    if (!ok && lane == 0) st->reason = -101;                   // peer exchange timed out
+}
+
 // ---- scalar steps of KSPSolve_CG (PETSc 3.6 cg.c), executed by one thread -------------------------------------
 
 __device__ int converged_default(CgState *st, int it, double rnorm)
@@ -315,6 +384,12 @@ int build_solver_structures(pfem_solver *h)
     PFEM_CUDA(cudaMemsetAsync(h->x.p, 0, nv * sizeof(double), s));
     PFEM_CUDA(cudaMemsetAsync(h->p.p, 0, nv * sizeof(double), s));
     PFEM_CUDA(cudaMemsetAsync(h->w.p, 0, nv * sizeof(double), s));
+    if (h->nranks > 1) {
+        // peers still map the previous ghost buffer: everybody unmaps before anybody frees
+        comm_p2p_teardown(h, false);
+        std::vector<int> sync;
+        PFEM_TRY(comm_allgather_int(h, 0, sync));
+    }
     PFEM_TRY(h->ghost_buf.alloc((size_t)h->n_ghost + 1));
     PFEM_TRY(h->partials.alloc((size_t)4 * h->sm_count * 16));
     if (!h->cg.p) {
@@ -349,6 +424,7 @@ int build_solver_structures(pfem_solver *h)
         PFEM_TRY(h->send_idx.alloc(sidx.size() + 1));
         PFEM_TRY(h->send_buf.alloc(sidx.size() + 1));
         if (!sidx.empty()) PFEM_CUDA(cudaMemcpy(h->send_idx.p, sidx.data(), sidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        PFEM_TRY(comm_p2p_setup(h));
     }
     PFEM_CUDA(cudaStreamSynchronize(s));
     return PFEM_OK;
@@ -372,9 +448,10 @@ __global__ void __launch_bounds__(CG_THREADS)
 cg_setup_kernel(int nloc, int row_lo, int pc_type, const int *__restrict__ rowptr, const int *__restrict__ col,
                 const double *__restrict__ val, const double *__restrict__ b, double *__restrict__ x,
                 double *__restrict__ r, double *__restrict__ z, double *__restrict__ dinv, double *__restrict__ partials,
-                int pstride, CgState *st, int finalize)
+                int pstride, CgState *st, int finalize /*0: publish red, 1: finalise, 2: peer all-reduce + finalise*/,
+                const P2pCtx *ctx)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     double zz = 0.0, zr = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += gridDim.x * blockDim.x) {
         double d = 0.0;
@@ -394,8 +471,15 @@ cg_setup_kernel(int nloc, int row_lo, int pc_type, const int *__restrict__ rowpt
     zr = block_sum(zr, sh);
     if (threadIdx.x == 0) { partials[blockIdx.x] = zz; partials[pstride + blockIdx.x] = zr; }
     if (last_block(&st->ticket[0])) {
-        const double a = reduce_partials(partials, gridDim.x, sh);
-        const double c = reduce_partials(partials + pstride, gridDim.x, sh);
+        double a = reduce_partials(partials, gridDim.x, sh);
+        double c = reduce_partials(partials + pstride, gridDim.x, sh);
+        if (finalize == 2) {
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                a = __shfl_sync(0xffffffffu, a, 0); c = __shfl_sync(0xffffffffu, c, 0);
+                p2p_allreduce2(ctx, st, 1, (st->seq << 32), a, c, sh);
+            }
+        }
         if (threadIdx.x == 0) {
             st->ticket[0] = 0;
             if (finalize) step_after_setup(st, a, c);
@@ -494,6 +578,70 @@ spmv_offdiag_kernel(int n_brows, const int *__restrict__ brow_ids, const int *__
     }
 }
 
+
+// Peer-memory halo: write this rank's boundary values of p straight into the owners' ghost buffers over NVLink, then
+// (last CTA) raise this rank's flag in every neighbour's exchange area.  Replaces pack + ncclSend/ncclRecv.
+__global__ void __launch_bounds__(CG_THREADS)
+halo_push_kernel(int n, const int *__restrict__ idx, const double *__restrict__ p, double *const *__restrict__ dst,
+                 CgState *st, const P2pCtx *ctx)
+{
+    if (st->reason != 0) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) st_relaxed_sys_f64(dst[i], p[idx[i]]);
+    __threadfence_system();
+    if (last_block(&st->ticket2[0])) {
+        __threadfence_system();
+        const unsigned long long tag = p2p_tag(st, 1);
+        if (threadIdx.x < ctx->nranks && ctx->sends_to[threadIdx.x]) st_release_sys(&ctx->mail[threadIdx.x]->halo_flag[ctx->rank], tag);
+        if (threadIdx.x == 0) st->ticket2[0] = 0;
+    }
+}
+
+// w[brow] += B ghost once every neighbour's values have landed; the last CTA then all-reduces p.w through the peers'
+// mailboxes and executes the scalar step.  Replaces spmv_offdiag_kernel + ncclAllReduce + scalar kernel.
+__global__ void __launch_bounds__(CG_THREADS)
+spmv_offdiag_p2p_kernel(int n_brows, const int *__restrict__ brow_ids, const int *__restrict__ brow_ptr,
+                        const int *__restrict__ bcol, const double *__restrict__ bval, const double *ghost,
+                        const double *__restrict__ p, double *__restrict__ w, double *__restrict__ partials, CgState *st,
+                        const P2pCtx *ctx)
+{
+    __shared__ double sh[64];
+    __shared__ int halo_ok;
+    if (st->reason != 0) return;
+    if (threadIdx.x == 0) halo_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < ctx->nranks && ctx->recvs_from[threadIdx.x]) {
+        if (!p2p_wait(&ctx->mail[ctx->rank]->halo_flag[threadIdx.x], p2p_tag(st, 1))) halo_ok = 0;
+    }
+    __syncthreads();
+    double pw = 0.0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_brows; q += gridDim.x * blockDim.x) {
+        double sum = 0.0;
+        for (int k = brow_ptr[q]; k < brow_ptr[q + 1]; k++) sum = fma(bval[k], __ldcg(ghost + bcol[k]), sum);
+        const int r = brow_ids[q];
+        w[r] += sum;
+        pw = fma(p[r], sum, pw);
+    }
+    pw = block_sum(pw, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = pw;
+    const int bad = halo_ok ? 0 : 1;
+    if (last_block(&st->ticket[2])) {
+        double t = reduce_partials(partials, gridDim.x, sh);
+        double dummy = 0.0;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            t = __shfl_sync(0xffffffffu, t, 0) + st->red[2];
+            p2p_allreduce2(ctx, st, 0, p2p_tag(st, 2), t, dummy, sh);
+        }
+        if (threadIdx.x == 0) {
+            st->ticket[2] = 0;
+            if (bad) st->reason = -101;
+            if (st->reason == 0) step_after_spmv(st, t);
+        }
+    } else if (bad && threadIdx.x == 0) {
+        st->reason = -101;
+    }
+}
+
 __global__ void pack_halo_kernel(int n, const int *__restrict__ idx, const double *__restrict__ p, double *__restrict__ buf,
                                  const CgState *__restrict__ st)
 {
@@ -505,9 +653,9 @@ __global__ void pack_halo_kernel(int n, const int *__restrict__ idx, const doubl
 __global__ void __launch_bounds__(CG_THREADS)
 cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__ w, const double *__restrict__ dinv,
                  double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ partials,
-                 int pstride, CgState *st, int finalize)
+                 int pstride, CgState *st, int finalize, const P2pCtx *ctx)
 {
-    __shared__ double sh[32];
+    __shared__ double sh[64];
     if (st->reason != 0) return;
     const double a = st->a;
     double zz = 0.0, zr = 0.0;
@@ -535,8 +683,15 @@ cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__
     zr = block_sum(zr, sh);
     if (threadIdx.x == 0) { partials[blockIdx.x] = zz; partials[pstride + blockIdx.x] = zr; }
     if (last_block(&st->ticket[3])) {
-        const double s0 = reduce_partials(partials, gridDim.x, sh);
-        const double s1 = reduce_partials(partials + pstride, gridDim.x, sh);
+        double s0 = reduce_partials(partials, gridDim.x, sh);
+        double s1 = reduce_partials(partials + pstride, gridDim.x, sh);
+        if (finalize == 2) {
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                s0 = __shfl_sync(0xffffffffu, s0, 0); s1 = __shfl_sync(0xffffffffu, s1, 0);
+                p2p_allreduce2(ctx, st, 1, p2p_tag(st, 3), s0, s1, sh);
+            }
+        }
         if (threadIdx.x == 0) {
             st->ticket[3] = 0;
             if (finalize) step_after_update(st, s0, s1);
@@ -607,13 +762,17 @@ int cg_solve(pfem_solver *h)
     CgState init;
     memset(&init, 0, sizeof init);
     init.rtol = h->rtol; init.abstol = h->abstol; init.dtol = h->dtol; init.max_it = h->max_it;
-    init.iter = multi ? -1 : 0;
+    init.iter = (multi && !h->p2p) ? -1 : 0;
+    init.seq = ++h->solve_seq;
     PFEM_CUDA(cudaMemcpyAsync(h->cg.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
     const int gv = grid_for(h, nloc, 2);
+    const bool p2p = multi && h->p2p;
+    const P2pCtx *ctx = p2p ? h->p2p_ctx.p : nullptr;
     cg_setup_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->row_lo, h->pc_type, h->rowptr.p, h->col.p, h->val.p, h->rhs.p, h->x.p,
-                                              h->r.p, h->z.p, h->dinv.p, h->partials.p, pstride, h->cg.p, multi ? 0 : 1);
+                                              h->r.p, h->z.p, h->dinv.p, h->partials.p, pstride, h->cg.p,
+                                              p2p ? 2 : (multi ? 0 : 1), ctx);
     h->launches++;
-    if (multi) {
+    if (multi && !p2p) {
         PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 2, s));
         scalar_after_setup_kernel<<<1, 1, 0, s>>>(h->cg.p);
         h->launches++;
@@ -628,6 +787,16 @@ int cg_solve(pfem_solver *h)
             h->launches++;
             if (!multi) {
                 PFEM_TRY(launch_spmv(h, 1));
+            } else if (p2p) {
+                // halo values go straight into the neighbours' ghost buffers; the diagonal block multiplies meanwhile
+                halo_push_kernel<<<grid_for(h, n_send > 0 ? n_send : 1, 1), CG_THREADS, 0, s>>>(n_send, h->send_idx.p, h->p.p, h->send_dst.p,
+                                                                                            h->cg.p, ctx);
+                h->launches++;
+                PFEM_TRY(launch_spmv(h, 2));
+                spmv_offdiag_p2p_kernel<<<grid_for(h, h->n_brows > 0 ? h->n_brows : 1, 1), CG_THREADS, 0, s>>>(
+                    h->n_brows, h->brow_ids.p, h->brow_ptr.p, h->bcol.p, h->bval.p, h->ghost_buf.p, h->p.p, h->w.p,
+                    h->partials.p + 3 * pstride, h->cg.p, ctx);
+                h->launches++;
             } else {
                 // halo: pack boundary values, exchange on the comm stream while the diagonal block multiplies
                 if (n_send > 0) {
@@ -649,9 +818,9 @@ int cg_solve(pfem_solver *h)
                 h->launches++;
             }
             cg_update_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->p.p, h->w.p, h->dinv.p, h->x.p, h->r.p, h->z.p, h->partials.p,
-                                                       pstride, h->cg.p, multi ? 0 : 1);
+                                                       pstride, h->cg.p, p2p ? 2 : (multi ? 0 : 1), ctx);
             h->launches++;
-            if (multi) {
+            if (multi && !p2p) {
                 PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 2, s));
                 scalar_after_update_kernel<<<1, 1, 0, s>>>(h->cg.p);
                 h->launches++;

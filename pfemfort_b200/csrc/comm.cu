@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
@@ -194,6 +195,111 @@ int comm_allgatherv_double(pfem_solver *h, const double *local, double *global_d
         PFEM_NCCL(h, h->nccl->Broadcast(local, global_dev + h->row_starts[q], cnt, ncclFloat64, q, comm, s));
     }
     PFEM_NCCL(h, h->nccl->GroupEnd());
+    return PFEM_OK;
+}
+
+// ---- peer-memory (CUDA IPC over NVLink) set-up ------------------------------------------------------------------------
+// Every rank exports its exchange area and its ghost buffer; the handles travel through one NCCL all-gather; each rank
+// maps the peers' buffers and precomputes, for every packed halo entry, the address inside the owner's ghost buffer.
+// Any failure (no peer access, IPC unavailable) leaves h->p2p false on ALL ranks and the NCCL path is used.
+
+void comm_p2p_teardown(pfem_solver *h, bool final)
+{
+    for (int q = 0; q < h->nranks && q < P2P_MAX_RANKS; q++) {
+        if (q == h->rank) continue;
+        if (h->peer_ghost[q]) cudaIpcCloseMemHandle(h->peer_ghost[q]);
+        h->peer_ghost[q] = nullptr;
+        if (final && h->peer_mail[q]) { cudaIpcCloseMemHandle(h->peer_mail[q]); h->peer_mail[q] = nullptr; }
+    }
+    if (final) {
+        h->peer_mail_open = false;
+        if (h->mail) cudaFree(h->mail);
+        h->mail = nullptr;
+    }
+    h->p2p = false;
+}
+
+int comm_p2p_setup(pfem_solver *h)
+{
+    const int P = h->nranks, me = h->rank;
+    h->p2p = false;
+    if (P == 1 || P > P2P_MAX_RANKS) return PFEM_OK;
+    const char *env = getenv("PFEM_COMM");
+    const bool want = !(env && strcmp(env, "nccl") == 0);
+    cudaStream_t s = h->stream;
+    ncclComm_t comm = (ncclComm_t)h->comm;
+    int ok = want ? 1 : 0;
+    if (ok && !h->mail) {
+        if (cudaMalloc((void **)&h->mail, sizeof(P2pMail)) != cudaSuccess) { cudaGetLastError(); ok = 0; h->mail = nullptr; }
+        else cudaMemset(h->mail, 0, sizeof(P2pMail));
+    }
+    // handles: [mail | ghost] per rank
+    struct Pack { cudaIpcMemHandle_t mail, ghost; int ok; int pad[3]; };
+    Pack mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaIpcGetMemHandle(&mine.mail, h->mail) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    if (ok && cudaIpcGetMemHandle(&mine.ghost, h->ghost_buf.p) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    mine.ok = ok;
+    DevBuf<Pack> dall;
+    PFEM_TRY(dall.alloc(P));
+    PFEM_CUDA(cudaMemcpyAsync(dall.p + me, &mine, sizeof(Pack), cudaMemcpyHostToDevice, s));
+    PFEM_NCCL(h, h->nccl->AllGather(dall.p + me, dall.p, sizeof(Pack), ncclInt8, comm, s));
+    std::vector<Pack> all(P);
+    PFEM_CUDA(cudaMemcpyAsync(all.data(), dall.p, sizeof(Pack) * P, cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    for (int q = 0; q < P; q++) ok = ok && all[q].ok;
+    if (ok) {
+        for (int q = 0; q < P && ok; q++) {
+            if (q == me) { h->peer_mail[q] = h->mail; h->peer_ghost[q] = h->ghost_buf.p; continue; }
+            if (!h->peer_mail[q]) {
+                void *ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[q].mail, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+                h->peer_mail[q] = (P2pMail *)ptr;
+            }
+            void *gp = nullptr;
+            if (cudaIpcOpenMemHandle(&gp, all[q].ghost, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            h->peer_ghost[q] = (double *)gp;
+        }
+    }
+    // every rank must take the same path
+    std::vector<int> oks;
+    PFEM_TRY(comm_allgather_int(h, ok, oks));
+    for (int v : oks) ok = ok && v;
+    if (!ok) {
+        for (int q = 0; q < P; q++) {
+            if (q != me && h->peer_ghost[q]) cudaIpcCloseMemHandle(h->peer_ghost[q]);
+            h->peer_ghost[q] = nullptr;
+        }
+        return PFEM_OK;
+    }
+    // where do my values land in peer q's ghost buffer?  q's recv_displs[me]
+    std::vector<int> send(P), ones(P, 1), recv, rc;
+    for (int q = 0; q < P; q++) send[q] = h->recv_displs[q];
+    PFEM_TRY(comm_alltoallv_int(h, send, ones, recv, rc));      // self entry is skipped by the exchange
+    std::vector<int> their_displ(P, 0);
+    {
+        // comm_alltoallv_int leaves the self slot untouched in the packed receive buffer: rebuild by rank
+        size_t o = 0;
+        for (int q = 0; q < P; q++) { their_displ[q] = (q == me) ? 0 : recv[o]; o += 1; }
+    }
+    const int n_send = h->send_displs[P];
+    std::vector<double *> dst((size_t)n_send + 1, nullptr);
+    for (int q = 0; q < P; q++)
+        for (int i = h->send_displs[q]; i < h->send_displs[q + 1]; i++)
+            dst[i] = h->peer_ghost[q] + their_displ[q] + (i - h->send_displs[q]);
+    PFEM_TRY(h->send_dst.alloc((size_t)n_send + 1));
+    PFEM_CUDA(cudaMemcpy(h->send_dst.p, dst.data(), ((size_t)n_send + 1) * sizeof(double *), cudaMemcpyHostToDevice));
+    P2pCtx ctx;
+    memset(&ctx, 0, sizeof ctx);
+    ctx.rank = me; ctx.nranks = P; ctx.seq = 0;
+    for (int q = 0; q < P; q++) {
+        ctx.mail[q] = h->peer_mail[q];
+        ctx.sends_to[q] = (q != me && h->send_counts[q] > 0) ? 1 : 0;
+        ctx.recvs_from[q] = (q != me && h->recv_counts[q] > 0) ? 1 : 0;
+    }
+    PFEM_TRY(h->p2p_ctx.alloc(1));
+    PFEM_CUDA(cudaMemcpy(h->p2p_ctx.p, &ctx, sizeof ctx, cudaMemcpyHostToDevice));
+    h->p2p = true;
     return PFEM_OK;
 }
 

@@ -61,9 +61,25 @@ struct CgState {
     double red[4];          // reduction landing zone (local sums; all-reduced in place for nranks > 1)
     int its, reason, iter, max_it;
     unsigned int ticket[4]; // last-block-done counters
+    unsigned int ticket2[4];
+    unsigned long long seq; // solve sequence number: high half of every peer-exchange tag
 };
 
 struct NcclApi;             // comm.cu
+
+// Peer-memory (NVLink) exchange area of one rank; every peer maps it through CUDA IPC and writes into it directly.
+constexpr int P2P_MAX_RANKS = 16;
+struct P2pMail {
+    unsigned long long halo_flag[P2P_MAX_RANKS];        // peer q: "my boundary values for tag t are in your ghost buffer"
+    unsigned long long red_flag[2][P2P_MAX_RANKS];      // [phase][peer]
+    double red_val[2][P2P_MAX_RANKS][2];                // [phase][peer][value]
+};
+struct P2pCtx {
+    int rank, nranks;
+    unsigned long long seq;                             // solve sequence number (high half of every tag)
+    P2pMail *mail[P2P_MAX_RANKS];                       // mail[rank] is the local one
+    int sends_to[P2P_MAX_RANKS], recvs_from[P2P_MAX_RANKS];
+};
 
 // SELL-32 storage of the diagonal block (columns owned by this rank), built at pattern time.
 struct SellMatrix {
@@ -147,6 +163,15 @@ struct pfem_solver {
     // communicator
     pfem::NcclApi *nccl = nullptr;
     void *comm = nullptr;
+    // peer-memory path (nranks > 1, all ranks on one NVLink/NVSwitch box)
+    bool p2p = false;
+    pfem::P2pMail *mail = nullptr;                       // own exchange area (cudaMalloc, IPC-exported)
+    pfem::P2pMail *peer_mail[pfem::P2P_MAX_RANKS] = {};
+    double *peer_ghost[pfem::P2P_MAX_RANKS] = {};
+    bool peer_mail_open = false;
+    pfem::DevBuf<pfem::P2pCtx> p2p_ctx;
+    pfem::DevBuf<double *> send_dst;                     // per packed halo entry: address inside the peer's ghost buffer
+    unsigned long long solve_seq = 0;
 };
 
 namespace pfem {
@@ -177,6 +202,8 @@ int comm_alltoallv_int(pfem_solver *h, const std::vector<int> &sendbuf, const st
 int comm_halo_exchange(pfem_solver *h, const double *sendbuf, double *recvbuf, cudaStream_t s);
 int comm_allreduce_sum(pfem_solver *h, double *buf, int n, cudaStream_t s);
 int comm_allgatherv_double(pfem_solver *h, const double *local, double *global_dev, cudaStream_t s);
+int comm_p2p_setup(pfem_solver *h);
+void comm_p2p_teardown(pfem_solver *h, bool final);
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -273,6 +273,11 @@ class SolverB200:
         _chk(self._lib.pfem_solver_get_info(self._h, C.byref(its), C.byref(reason), C.byref(rnorm), C.byref(ta), C.byref(ts)))
         return dict(its=its.value, reason=reason.value, rnorm=rnorm.value, t_assemble=ta.value, t_solve=ts.value)
 
+    def comm_mode(self) -> int:
+        m = C.c_int()
+        _chk(self._lib.pfem_solver_comm_mode(self._h, C.byref(m)))
+        return m.value
+
     def launch_count(self, reset: bool = False) -> int:
         n = C.c_longlong()
         _chk(self._lib.pfem_solver_launch_count(self._h, C.byref(n), 1 if reset else 0))

@@ -88,6 +88,7 @@ def main():
         rp, col, val = s.get_csr()
         rhs = s.get_rhs()
         x = s.get_solution()
+        result["comm_mode"] = s.comm_mode()
         parts = [None] * world
         dist.all_gather_object(parts, (rp, col, val, rhs, info["its"], info["reason"]))
         if rank == 0:

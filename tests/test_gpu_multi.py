@@ -17,15 +17,18 @@ def _ngpu():
 
 @pytest.mark.parametrize("mesh,nproc,port", [("tet10", 2, 29621), ("beam3Dtet6366", 2, 29622), ("cookmembranetria32", 2, 29623),
                                              ("gen_tet24", 2, 29624), ("gen_tet24", 4, 29625), ("gen_tet24", 8, 29626)])
-def test_multi_gpu_matches_oracle(gpu, tmp_path, mesh, nproc, port):
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
+def test_multi_gpu_matches_oracle(gpu, tmp_path, mesh, nproc, port, comm):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
+    os.environ["PFEM_COMM"] = comm          # p2p: peer-memory kernels over NVLink (default); nccl: the NCCL path
     out = os.path.join(str(tmp_path), "result.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), "--mode", "gpu", "--mesh", mesh, "--out", out]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.load(open(out))
+    assert res["comm_mode"] == (2 if comm == "p2p" else 1)
     assert res["pattern_bit_identical"] and res["values_bit_identical"] and res["rhs_bit_identical"]
     assert all(x == res["oracle_reason"] == 2 for x in res["reason"])
     assert len(set(res["its"])) == 1
