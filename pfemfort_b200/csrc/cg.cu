@@ -12,9 +12,15 @@
 //    (fixed-order sum of the per-CTA partials => run-to-run deterministic); kernels early-out once
 //    `reason` is set, so the host only polls every few iterations and never stalls the pipeline.
 //  * Per iteration: direction (p = z + b p), SpMV fused with p.w, update (x, r, z, z.z, z.r fused).
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "internal.cuh"
+
+namespace cgx = cooperative_groups;
 
 namespace pfem {
 
@@ -108,7 +114,7 @@ __device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigne
 
 // All-reduce (sum) of two doubles across the ranks through the peers' mailboxes, executed by the FIRST WARP of one CTA.
 // Every rank sums the P contributions in rank order, so all ranks obtain bit-identical results.
-__device__ __forceinline__ void p2p_allreduce2(const P2pCtx *c, CgState *st, int phase, unsigned long long tag, double &v0,
+__device__ __forceinline__ bool p2p_allreduce2(const P2pCtx *c, CgState *st, int phase, unsigned long long tag, double &v0,
                                                double &v1, double *sh)
 {
     const int lane = threadIdx.x;      // caller guarantees threadIdx.x < 32
@@ -132,7 +138,8 @@ __device__ __forceinline__ void p2p_allreduce2(const P2pCtx *c, CgState *st, int
     double s0 = 0.0, s1 = 0.0;
     for (int q = 0; q < P; q++) { s0 += sh[2 * q]; s1 += sh[2 * q + 1]; }
     v0 = s0; v1 = s1;
-    if (!ok && lane == 0) st->reason = -101;                   // peer exchange timed out
+    if (!ok && lane == 0 && st) st->reason = -101;             // peer exchange timed out
+    return ok;
 }
 
 // ---- scalar steps of KSPSolve_CG (PETSc 3.6 cg.c), executed by one thread -------------------------------------
@@ -305,7 +312,8 @@ int build_solver_structures(pfem_solver *h)
     cudaStream_t s = h->stream;
     const int nloc = h->size_local, G = h->sm_count * 8;
     const int nslices = (nloc + 31) / 32, nrows_padded = nslices * 32;
-    DevBuf<int> ndiag, noff, off_ptr, flags, brow_rank;
+    DevBuf<int> ndiag, noff, flags, brow_rank;
+    DevBuf<int> &off_ptr = h->off_ptr;
     DevBuf<long long> slice_sz;
     PFEM_TRY(ndiag.alloc((size_t)nloc + 1));
     PFEM_TRY(noff.alloc((size_t)nloc + 1));
@@ -700,6 +708,309 @@ cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__
     }
 }
 
+
+// =====================================================================================================================
+// Persistent CG: the whole KSPSolve in ONE cooperative kernel per GPU.
+//
+// Kernel boundaries cost ~9 us each on this part (launch gap + last-CTA reduction tail), i.e. ~30 us of a 390 us
+// iteration on one GPU and most of a 50 us iteration on eight.  Here every CTA stays resident for the entire solve;
+// the three phases of an iteration (direction | SpMV + p.w | update + z.z, z.r) are separated by grid barriers, CTA 0
+// finishes each reduction in a fixed order (and, for nranks > 1, all-reduces it through the peers' NVLink mailboxes)
+// and republishes it through a flag in local memory; the CG scalars live in registers, identically in every CTA.
+// For nranks > 1 the halo is pushed into the neighbours' ghost buffers right after the direction phase; SpMV warps
+// whose slice has off-diagonal entries wait for the neighbours' flags, all others never wait.
+// =====================================================================================================================
+
+struct PcgArgs {
+    int nloc, nslices, row_lo, pc_type, has_off, multi, pstride, n_send;
+    const long long *slice_off; const int *scol; const double *sval;
+    const int *off_ptr; const int *bcol; const double *bval; const double *ghost;
+    const int *rowptr; const int *col; const double *val;
+    const double *b;
+    double *x, *r, *z, *p, *w, *dinv;
+    double *partials;
+    CgState *st;
+    const P2pCtx *ctx;
+    const int *send_idx; double *const *send_dst;
+    double *bcast;                         // [0..1] values, [2] ok flag
+    unsigned long long *bcast_flag;        // tag of the last published reduction
+    unsigned int *push_ticket;             // monotonically increasing CTA arrival counter of the halo pushes
+};
+
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.global.release.gpu.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Finish a reduction whose per-CTA partials are in `partials` (+ second array at pstride when two values): CTA 0
+// sums them in a fixed order, all-reduces across ranks if needed, and republishes; every thread returns the result.
+__device__ __forceinline__ bool pcg_reduce(const PcgArgs &a, const double *part0, const double *part1, int phase,
+                                           unsigned long long ptag, unsigned long long &bseq, double &v0, double &v1,
+                                           double *sh, double *s_bc)
+{
+    bseq++;
+    if (blockIdx.x == 0) {
+        double t0 = reduce_partials(part0, gridDim.x, sh);
+        double t1 = part1 ? reduce_partials(part1, gridDim.x, sh) : 0.0;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            t0 = __shfl_sync(0xffffffffu, t0, 0); t1 = __shfl_sync(0xffffffffu, t1, 0);
+            bool ok = true;
+            if (a.multi) ok = p2p_allreduce2(a.ctx, nullptr, phase, ptag, t0, t1, sh);
+            if (threadIdx.x == 0) {
+                a.bcast[0] = t0; a.bcast[1] = t1; a.bcast[2] = ok ? 1.0 : 0.0;
+                __threadfence();
+                st_release_gpu(a.bcast_flag, bseq);
+                s_bc[0] = t0; s_bc[1] = t1; s_bc[2] = ok ? 1.0 : 0.0;
+            }
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) {
+            const long long c0 = clock64();
+            bool ok = true;
+            while (ld_acquire_gpu(a.bcast_flag) != bseq) {
+                if (clock64() - c0 > 40000000000LL) { ok = false; break; }
+            }
+            s_bc[0] = __ldcg(a.bcast); s_bc[1] = __ldcg(a.bcast + 1); s_bc[2] = ok ? __ldcg(a.bcast + 2) : 0.0;
+        }
+        __syncthreads();
+    }
+    v0 = s_bc[0]; v1 = s_bc[1];
+    return s_bc[2] != 0.0;
+}
+
+__global__ void __launch_bounds__(CG_THREADS, 5)
+cg_persistent_kernel(const PcgArgs a)
+{
+    cgx::grid_group grid = cgx::this_grid();
+    __shared__ double sh[64];
+    __shared__ double s_bc[4];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    const int nloc = a.nloc;
+    double *part_zz = a.partials, *part_zr = a.partials + a.pstride, *part_pw = a.partials + 2 * a.pstride;
+    unsigned long long bseq = 0;
+    unsigned int pushes = 0;
+
+    // the CG scalars: one copy per CTA in shared memory, advanced identically in every CTA by its thread 0
+    __shared__ CgState ls;
+    if (threadIdx.x == 0) {
+        ls.rtol = a.st->rtol; ls.abstol = a.st->abstol; ls.dtol = a.st->dtol; ls.max_it = a.st->max_it; ls.seq = a.st->seq;
+        ls.beta = ls.betaold = ls.dpi = ls.dpiold = ls.dp = ls.a = ls.b = ls.ttol = ls.rnorm0 = 0.0;
+        ls.its = 0; ls.reason = 0; ls.iter = 0;
+    }
+    __syncthreads();
+
+    // ---- set-up: PCSetUp_Jacobi, x = 0, r = b, z = M^-1 r, (z.z, z.r) ----
+    {
+        double zz = 0.0, zr = 0.0;
+        for (int i = gtid; i < nloc; i += gthreads) {
+            double d = 0.0;
+            int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+            const int end = hi, c = a.row_lo + i;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a.col[mid] < c) lo = mid + 1; else hi = mid;
+            }
+            if (lo < end && a.col[lo] == c) d = a.val[lo];
+            const double di = a.pc_type == PFEM_PC_JACOBI ? (d == 0.0 ? 1.0 : 1.0 / d) : 1.0;
+            const double ri = a.b[i], zi = ri * di;
+            a.dinv[i] = di; a.x[i] = 0.0; a.r[i] = ri; a.z[i] = zi;
+            zz += zi * zi; zr += zi * ri;
+        }
+        zz = block_sum(zz, sh);
+        zr = block_sum(zr, sh);
+        if (threadIdx.x == 0) { part_zz[blockIdx.x] = zz; part_zr[blockIdx.x] = zr; }
+        grid.sync();
+        const bool ok = pcg_reduce(a, part_zz, part_zr, 1, ls.seq << 32, bseq, zz, zr, sh, s_bc);
+        if (threadIdx.x == 0) {
+            step_after_setup(&ls, zz, zr);
+            if (!ok) ls.reason = -101;
+        }
+        __syncthreads();
+    }
+
+    while (ls.reason == 0) {
+        // ---- direction: p = z + b p ----
+        {
+            const bool first = ls.iter == 0;
+            const double b = ls.b;
+            const int n2 = nloc >> 1;
+            const double2 *z2 = reinterpret_cast<const double2 *>(a.z);
+            double2 *p2 = reinterpret_cast<double2 *>(a.p);
+            for (int i = gtid; i < n2; i += gthreads) {
+                const double2 zv = z2[i];
+                double2 pv;
+                if (first) pv = zv;
+                else { pv = p2[i]; pv.x = zv.x + b * pv.x; pv.y = zv.y + b * pv.y; }
+                p2[i] = pv;
+            }
+            if ((nloc & 1) && gtid == 0) a.p[nloc - 1] = first ? a.z[nloc - 1] : a.z[nloc - 1] + b * a.p[nloc - 1];
+        }
+        grid.sync();
+        // ---- halo push (nranks > 1): boundary values straight into the neighbours' ghost buffers ----
+        const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 1u);
+        if (a.multi) {
+            for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], a.p[a.send_idx[i]]);
+            __threadfence_system();
+            __syncthreads();
+            pushes++;
+            if (threadIdx.x == 0) {
+                const unsigned int t = atomicAdd(a.push_ticket, 1u);
+                s_bc[3] = (t == gridDim.x * pushes - 1u) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            if (s_bc[3] != 0.0) {
+                __threadfence_system();
+                if (threadIdx.x < a.ctx->nranks && a.ctx->sends_to[threadIdx.x])
+                    st_release_sys(&a.ctx->mail[threadIdx.x]->halo_flag[a.ctx->rank], htag);
+            }
+        }
+        // ---- SpMV: w = A_diag p (+ B ghost), fused with p.w ----
+        {
+            double pw = 0.0;
+            bool halo_ready = false, halo_ok = true;
+            for (int s = gwarp; s < a.nslices; s += gwarps) {
+                const long long o0 = a.slice_off[s], o1 = a.slice_off[s + 1];
+                const int width = (int)((o1 - o0) >> 5);
+                const int *cp = a.scol + o0 + lane;
+                const double *vp = a.sval + o0 + lane;
+                double sum = 0.0;
+                int k = 0;
+                for (; k + 4 <= width; k += 4) {
+                    const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32);
+                    const int c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
+                    const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32);
+                    const double v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
+                    const double x0 = a.p[c0], x1 = a.p[c1], x2 = a.p[c2], x3 = a.p[c3];
+                    sum = fma(v0, x0, sum); sum = fma(v1, x1, sum); sum = fma(v2, x2, sum); sum = fma(v3, x3, sum);
+                }
+                for (; k < width; k++) sum = fma(__ldcs(vp + k * 32), a.p[__ldcs(cp + k * 32)], sum);
+                const int r = s * 32 + lane;
+                if (a.has_off) {
+                    int lo = 0, hi = 0;
+                    if (r < nloc) { lo = a.off_ptr[r]; hi = a.off_ptr[r + 1]; }
+                    if (__any_sync(0xffffffffu, hi > lo)) {
+                        if (!halo_ready) {       // first boundary slice of this warp in this iteration: wait for the neighbours
+                            bool okw = true;
+                            if (lane < a.ctx->nranks && a.ctx->recvs_from[lane])
+                                okw = p2p_wait(&a.ctx->mail[a.ctx->rank]->halo_flag[lane], htag);
+                            halo_ok = __all_sync(0xffffffffu, okw);
+                            halo_ready = true;
+                        }
+                        double osum = 0.0;
+                        for (int q = lo; q < hi; q++) osum = fma(a.bval[q], __ldcg(a.ghost + a.bcol[q]), osum);
+                        sum = sum + osum;
+                    }
+                }
+                if (r < nloc) {
+                    a.w[r] = sum;
+                    pw = fma(a.p[r], sum, pw);
+                }
+            }
+            pw = block_sum(pw, sh);
+            if (threadIdx.x == 0) part_pw[blockIdx.x] = halo_ok ? pw : __longlong_as_double(0x7ff8000000000000LL);
+            grid.sync();
+            double dummy;
+            const bool ok = pcg_reduce(a, part_pw, nullptr, 0, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 2u),
+                                       bseq, pw, dummy, sh, s_bc);
+            if (threadIdx.x == 0) {
+                step_after_spmv(&ls, pw);
+                if (!ok || pw != pw) ls.reason = -101;
+            }
+            __syncthreads();
+        }
+        if (ls.reason != 0) break;
+        // ---- update: x += a p, r -= a w, z = M^-1 r, (z.z, z.r) ----
+        {
+            const double al = ls.a;
+            double zz = 0.0, zr = 0.0;
+            const int n2 = nloc >> 1;
+            const double2 *p2 = reinterpret_cast<const double2 *>(a.p), *w2 = reinterpret_cast<const double2 *>(a.w);
+            const double2 *d2 = reinterpret_cast<const double2 *>(a.dinv);
+            double2 *x2 = reinterpret_cast<double2 *>(a.x), *r2 = reinterpret_cast<double2 *>(a.r), *z2 = reinterpret_cast<double2 *>(a.z);
+            for (int i = gtid; i < n2; i += gthreads) {
+                const double2 pv = p2[i], wv = w2[i], dv = d2[i];
+                double2 xv = x2[i], rv = r2[i], zv;
+                xv.x = fma(al, pv.x, xv.x); xv.y = fma(al, pv.y, xv.y);
+                rv.x = fma(-al, wv.x, rv.x); rv.y = fma(-al, wv.y, rv.y);
+                zv.x = rv.x * dv.x; zv.y = rv.y * dv.y;
+                x2[i] = xv; r2[i] = rv; z2[i] = zv;
+                zz = fma(zv.x, zv.x, zz); zz = fma(zv.y, zv.y, zz);
+                zr = fma(zv.x, rv.x, zr); zr = fma(zv.y, rv.y, zr);
+            }
+            if ((nloc & 1) && gtid == 0) {
+                const int i = nloc - 1;
+                const double xv = fma(al, a.p[i], a.x[i]), rv = fma(-al, a.w[i], a.r[i]), zv = rv * a.dinv[i];
+                a.x[i] = xv; a.r[i] = rv; a.z[i] = zv;
+                zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
+            }
+            zz = block_sum(zz, sh);
+            zr = block_sum(zr, sh);
+            if (threadIdx.x == 0) { part_zz[blockIdx.x] = zz; part_zr[blockIdx.x] = zr; }
+            grid.sync();
+            const bool ok = pcg_reduce(a, part_zz, part_zr, 1, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 3u),
+                                       bseq, zz, zr, sh, s_bc);
+            if (threadIdx.x == 0) {
+                step_after_update(&ls, zz, zr);
+                if (!ok) ls.reason = -101;
+            }
+            __syncthreads();
+        }
+    }
+    if (gtid == 0) {
+        a.st->its = ls.its; a.st->reason = ls.reason; a.st->iter = ls.iter; a.st->dp = ls.dp;
+        a.st->beta = ls.beta; a.st->a = ls.a; a.st->b = ls.b;
+    }
+}
+
+static int cg_solve_persistent(pfem_solver *h, bool &used)
+{
+    used = false;
+    const char *env = getenv("PFEM_CG");
+    if (env && strcmp(env, "kernels") == 0) return PFEM_OK;
+    if (h->nranks > 1 && !h->p2p) return PFEM_OK;            // the NCCL path needs host-launched collectives
+    if (h->profile) return PFEM_OK;                           // per-launch SpMV timing needs separate launches
+    int coop = 0;
+    PFEM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    if (!coop) return PFEM_OK;
+    int per_sm = 0;
+    PFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel, CG_THREADS, 0));
+    if (per_sm < 1) return PFEM_OK;
+    if (per_sm > 8) per_sm = 8;
+    const int grid = h->sm_count * per_sm;
+    if (grid > h->sm_count * 16) return PFEM_OK;
+    cudaStream_t s = h->stream;
+    if (!h->pcg_bcast.p) PFEM_TRY(h->pcg_bcast.alloc(8));
+    PFEM_CUDA(cudaMemsetAsync(h->pcg_bcast.p, 0, 8 * sizeof(double), s));
+    PcgArgs a;
+    memset(&a, 0, sizeof a);
+    a.nloc = h->size_local; a.nslices = h->A.nslices; a.row_lo = h->row_lo; a.pc_type = h->pc_type;
+    a.multi = h->nranks > 1 ? 1 : 0; a.has_off = (a.multi && h->nnz_off > 0) ? 1 : 0;
+    a.pstride = h->sm_count * 16; a.n_send = a.multi ? h->send_displs[h->nranks] : 0;
+    a.slice_off = h->A.slice_off.p; a.scol = h->A.col.p; a.sval = h->A.val.p;
+    a.off_ptr = h->off_ptr.p; a.bcol = h->bcol.p; a.bval = h->bval.p; a.ghost = h->ghost_buf.p;
+    a.rowptr = h->rowptr.p; a.col = h->col.p; a.val = h->val.p; a.b = h->rhs.p;
+    a.x = h->x.p; a.r = h->r.p; a.z = h->z.p; a.p = h->p.p; a.w = h->w.p; a.dinv = h->dinv.p;
+    a.partials = h->partials.p; a.st = h->cg.p; a.ctx = a.multi ? h->p2p_ctx.p : nullptr;
+    a.send_idx = h->send_idx.p; a.send_dst = h->send_dst.p;
+    a.bcast = h->pcg_bcast.p;
+    a.bcast_flag = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 4);
+    a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 6);
+    void *params[] = {(void *)&a};
+    PFEM_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), params, 0, s));
+    h->launches++;
+    used = true;
+    return PFEM_OK;
+}
+
 static int grid_for(pfem_solver *h, long long work_items, int per_thread)
 {
     long long blocks = (work_items + (long long)CG_THREADS * per_thread - 1) / ((long long)CG_THREADS * per_thread);
@@ -765,6 +1076,20 @@ int cg_solve(pfem_solver *h)
     init.iter = (multi && !h->p2p) ? -1 : 0;
     init.seq = ++h->solve_seq;
     PFEM_CUDA(cudaMemcpyAsync(h->cg.p, &init, sizeof init, cudaMemcpyHostToDevice, s));
+    bool persistent = false;
+    PFEM_TRY(cg_solve_persistent(h, persistent));
+    if (persistent) {
+        PFEM_CUDA(cudaMemcpyAsync(h->cg_host, h->cg.p, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaEventRecord(h->ev1, s));
+        PFEM_CUDA(cudaEventSynchronize(h->ev1));
+        PFEM_CUDA(cudaGetLastError());
+        float msp = 0.f;
+        PFEM_CUDA(cudaEventElapsedTime(&msp, h->ev0, h->ev1));
+        h->t_solve = msp * 1e-3;
+        h->its = h->cg_host->its; h->reason = h->cg_host->reason; h->rnorm = h->cg_host->dp;
+        if (h->reason == -101) { set_error("cg: peer exchange timed out"); return PFEM_ERR_NCCL; }
+        return PFEM_OK;
+    }
     const int gv = grid_for(h, nloc, 2);
     const bool p2p = multi && h->p2p;
     const P2pCtx *ctx = p2p ? h->p2p_ctx.p : nullptr;

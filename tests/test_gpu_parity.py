@@ -251,3 +251,30 @@ def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch):
             out.append((s.get_csr()[2], s.get_rhs()))
             s.free()
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_persistent_and_multi_kernel_cg_agree(gpu, input_dir, monkeypatch):
+    """The persistent cooperative CG kernel (default) and the launch-per-phase path follow the same PETSc
+    semantics: same reason, same iteration count, same solution to rounding."""
+    for name in ("tet10", "cookmembranetria32"):
+        m, kind = _load(name, input_dir)
+        num = D.number(m, kind)
+        res = []
+        for mode in ("persistent", "kernels"):
+            monkeypatch.setenv("PFEM_CG", mode)
+            s = S.SolverB200(0)
+            info = D.run_rank(s, m, num, rtol=1e-10)
+            res.append((info["its"], info["reason"], s.get_solution()))
+            s.free()
+        assert res[0][1] == res[1][1] == 2
+        assert abs(res[0][0] - res[1][0]) <= 1
+        assert np.abs(res[0][2] - res[1][2]).max() <= 1e-9 * np.abs(res[1][2]).max()
+    # max_it reached -> DIVERGED_ITS (-3) with its = max_it, on both paths
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    for mode in ("persistent", "kernels"):
+        monkeypatch.setenv("PFEM_CG", mode)
+        s = S.SolverB200(0)
+        info = D.run_rank(s, m, num, rtol=1e-10, max_it=7)
+        assert (info["its"], info["reason"]) == (7, -3)
+        s.free()
