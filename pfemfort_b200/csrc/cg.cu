@@ -112,33 +112,66 @@ __device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigne
     return true;
 }
 
-// All-reduce (sum) of two doubles across the ranks through the peers' mailboxes, executed by the FIRST WARP of one CTA.
-// Every rank sums the P contributions in rank order, so all ranks obtain bit-identical results.
-__device__ __forceinline__ bool p2p_allreduce2(const P2pCtx *c, CgState *st, int phase, unsigned long long tag, double &v0,
-                                               double &v1, double *sh)
+__device__ __forceinline__ void st_slot_sys(P2pSlot *p, double v, unsigned long long tag)
+{
+    asm volatile("st.global.relaxed.sys.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_slot_sys(const P2pSlot *p, double &v, unsigned long long &tag)
+{
+    long long bits;
+    asm volatile("ld.global.relaxed.sys.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(p) : "memory");
+    v = __longlong_as_double(bits);
+}
+
+// All-reduce (sum) of up to 4 doubles across the ranks through the peers' mailboxes, executed by the FIRST WARP of one
+// CTA.  Each contribution travels as one 16-byte {value, tag} store over NVLink (no fence, no separate flag); every
+// rank sums the P contributions in rank order, so all ranks obtain bit-identical results.
+template <int NV>
+__device__ __forceinline__ bool p2p_allreduce(const P2pCtx *c, CgState *st, int phase, unsigned long long tag, double (&v)[NV],
+                                              double *sh)
 {
     const int lane = threadIdx.x;      // caller guarantees threadIdx.x < 32
     const int P = c->nranks, me = c->rank;
     if (lane < P) {
         P2pMail *dst = c->mail[lane];
-        st_relaxed_sys_f64(&dst->red_val[phase][me][0], v0);
-        st_relaxed_sys_f64(&dst->red_val[phase][me][1], v1);
-        __threadfence_system();
-        st_release_sys(&dst->red_flag[phase][me], tag);
+#pragma unroll
+        for (int i = 0; i < NV; i++) st_slot_sys(&dst->red[phase][me][i], v[i], tag);
     }
     bool ok = true;
     if (lane < P) {
         const P2pMail *mine = c->mail[me];
-        ok = p2p_wait(&mine->red_flag[phase][lane], tag);
-        sh[2 * lane] = ld_volatile_f64(&mine->red_val[phase][lane][0]);
-        sh[2 * lane + 1] = ld_volatile_f64(&mine->red_val[phase][lane][1]);
+        const long long t0 = clock64();
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double val;
+            unsigned long long tg;
+            ld_slot_sys(&mine->red[phase][lane][i], val, tg);
+            while (tg != tag) {
+                if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a dead peer must not hang the GPU
+                ld_slot_sys(&mine->red[phase][lane][i], val, tg);
+            }
+            sh[NV * lane + i] = val;
+        }
     }
     ok = __all_sync(0xffffffffu, ok);
     __syncwarp();
-    double s0 = 0.0, s1 = 0.0;
-    for (int q = 0; q < P; q++) { s0 += sh[2 * q]; s1 += sh[2 * q + 1]; }
-    v0 = s0; v1 = s1;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s0 = 0.0;
+        for (int q = 0; q < P; q++) s0 += sh[NV * q + i];
+        v[i] = s0;
+    }
+    __syncwarp();
     if (!ok && lane == 0 && st) st->reason = -101;             // peer exchange timed out
+    return ok;
+}
+
+__device__ __forceinline__ bool p2p_allreduce2(const P2pCtx *c, CgState *st, int phase, unsigned long long tag, double &v0,
+                                               double &v1, double *sh)
+{
+    double v[2] = {v0, v1};
+    const bool ok = p2p_allreduce<2>(c, st, phase, tag, v, sh);
+    v0 = v[0]; v1 = v[1];
     return ok;
 }
 
@@ -388,7 +421,7 @@ int build_solver_structures(pfem_solver *h)
     // vectors (padded to whole slices so the SpMV tail needs no guards on reads)
     const size_t nv = (size_t)nrows_padded + 32;
     PFEM_TRY(h->x.alloc(nv)); PFEM_TRY(h->r.alloc(nv)); PFEM_TRY(h->z.alloc(nv));
-    PFEM_TRY(h->p.alloc(nv)); PFEM_TRY(h->w.alloc(nv)); PFEM_TRY(h->dinv.alloc(nv));
+    PFEM_TRY(h->p.alloc(nv)); PFEM_TRY(h->w.alloc(nv)); PFEM_TRY(h->dinv.alloc(nv)); PFEM_TRY(h->sv.alloc(nv));
     PFEM_CUDA(cudaMemsetAsync(h->x.p, 0, nv * sizeof(double), s));
     PFEM_CUDA(cudaMemsetAsync(h->p.p, 0, nv * sizeof(double), s));
     PFEM_CUDA(cudaMemsetAsync(h->w.p, 0, nv * sizeof(double), s));
@@ -732,8 +765,9 @@ struct PcgArgs {
     CgState *st;
     const P2pCtx *ctx;
     const int *send_idx; double *const *send_dst;
-    double *bcast;                         // [0..1] values, [2] ok flag
-    unsigned long long *bcast_flag;        // tag of the last published reduction
+    double *bcast;                         // [0..2] values, [3] ok flag
+    unsigned long long *bcast_flag;        // epoch of the last released barrier
+    unsigned long long *arrive;            // monotonically increasing CTA arrival counter of the barriers
     unsigned int *push_ticket;             // monotonically increasing CTA arrival counter of the halo pushes
 };
 
@@ -748,55 +782,77 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     return v;
 }
 
-// Finish a reduction whose per-CTA partials are in `partials` (+ second array at pstride when two values): CTA 0
-// sums them in a fixed order, all-reduces across ranks if needed, and republishes; every thread returns the result.
-__device__ __forceinline__ bool pcg_reduce(const PcgArgs &a, const double *part0, const double *part1, int phase,
-                                           unsigned long long ptag, unsigned long long &bseq, double &v0, double &v1,
-                                           double *sh, double *s_bc)
+// Grid-wide reduce-and-broadcast barrier.  Every CTA deposits its NV block sums and arrives on a monotonically increasing
+// counter; the LAST CTA to arrive sums all partials in a fixed order, all-reduces them across the ranks if needed
+// (one 16-byte NVLink store per value and peer), publishes the result and releases everybody through one flag.
+// One synchronisation per phase instead of "grid barrier, then reduce, then broadcast".  NV = 0: plain barrier.
+template <int NV>
+__device__ __forceinline__ bool pcg_sync(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
+                                         unsigned long long &epoch, double *sh, double *s_bc)
 {
-    bseq++;
-    if (blockIdx.x == 0) {
-        double t0 = reduce_partials(part0, gridDim.x, sh);
-        double t1 = part1 ? reduce_partials(part1, gridDim.x, sh) : 0.0;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            t0 = __shfl_sync(0xffffffffu, t0, 0); t1 = __shfl_sync(0xffffffffu, t1, 0);
-            bool ok = true;
-            if (a.multi) ok = p2p_allreduce2(a.ctx, nullptr, phase, ptag, t0, t1, sh);
-            if (threadIdx.x == 0) {
-                a.bcast[0] = t0; a.bcast[1] = t1; a.bcast[2] = ok ? 1.0 : 0.0;
-                __threadfence();
-                st_release_gpu(a.bcast_flag, bseq);
-                s_bc[0] = t0; s_bc[1] = t1; s_bc[2] = ok ? 1.0 : 0.0;
-            }
-        }
-        __syncthreads();
-    } else {
-        if (threadIdx.x == 0) {
-            const long long c0 = clock64();
-            bool ok = true;
-            while (ld_acquire_gpu(a.bcast_flag) != bseq) {
-                if (clock64() - c0 > 40000000000LL) { ok = false; break; }
-            }
-            s_bc[0] = __ldcg(a.bcast); s_bc[1] = __ldcg(a.bcast + 1); s_bc[2] = ok ? __ldcg(a.bcast + 2) : 0.0;
-        }
-        __syncthreads();
+    __shared__ int s_last;
+    epoch++;
+    __syncthreads();                       // every thread's global writes of this phase precede thread 0's fence
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) a.partials[i * a.pstride + blockIdx.x] = v[i];
+        __threadfence();
+        const unsigned long long t = atomicAdd(a.arrive, 1ULL);
+        s_last = (t == (unsigned long long)gridDim.x * epoch - 1ULL) ? 1 : 0;
     }
-    v0 = s_bc[0]; v1 = s_bc[1];
-    return s_bc[2] != 0.0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double r[NV > 0 ? NV : 1];
+        bool ok = true;
+        if (NV > 0) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) r[i] = reduce_partials(a.partials + i * a.pstride, gridDim.x, sh);
+            __syncthreads();
+            if (threadIdx.x < 32) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) r[i] = __shfl_sync(0xffffffffu, r[i], 0);
+                if (a.multi) ok = p2p_allreduce<(NV > 0 ? NV : 1)>(a.ctx, nullptr, phase, ptag, r, sh);
+            }
+        }
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) { a.bcast[i] = r[i]; s_bc[i] = r[i]; }
+            a.bcast[3] = ok ? 1.0 : 0.0; s_bc[3] = ok ? 1.0 : 0.0;
+            __threadfence();
+            st_release_gpu(a.bcast_flag, epoch);
+        }
+    } else if (threadIdx.x == 0) {
+        const long long c0 = clock64();
+        bool ok = true;
+        while (ld_acquire_gpu(a.bcast_flag) != epoch) {
+            if (clock64() - c0 > 40000000000LL) { ok = false; break; }       // ~20 s
+            __nanosleep(40);               // keep the pollers off the L2 slice that has to deliver the release
+        }
+        __threadfence();                   // gpu-scope fence: drops this SM's stale L1 lines before the next phase reads
+#pragma unroll
+        for (int i = 0; i < NV; i++) s_bc[i] = __ldcg(a.bcast + i);
+        s_bc[3] = ok ? __ldcg(a.bcast + 3) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = s_bc[i];
+    const bool okall = s_bc[3] != 0.0;
+    __syncthreads();                       // s_bc is reused by the next call
+    return okall;
 }
 
-__global__ void __launch_bounds__(CG_THREADS, 5)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 cg_persistent_kernel(const PcgArgs a)
 {
-    cgx::grid_group grid = cgx::this_grid();
     __shared__ double sh[64];
     __shared__ double s_bc[4];
+    __shared__ double s_push;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int nloc = a.nloc;
-    double *part_zz = a.partials, *part_zr = a.partials + a.pstride, *part_pw = a.partials + 2 * a.pstride;
-    unsigned long long bseq = 0;
+    unsigned long long epoch = 0;
     unsigned int pushes = 0;
 
     // the CG scalars: one copy per CTA in shared memory, advanced identically in every CTA by its thread 0
@@ -825,11 +881,11 @@ cg_persistent_kernel(const PcgArgs a)
             a.dinv[i] = di; a.x[i] = 0.0; a.r[i] = ri; a.z[i] = zi;
             zz += zi * zi; zr += zi * ri;
         }
-        zz = block_sum(zz, sh);
-        zr = block_sum(zr, sh);
-        if (threadIdx.x == 0) { part_zz[blockIdx.x] = zz; part_zr[blockIdx.x] = zr; }
-        grid.sync();
-        const bool ok = pcg_reduce(a, part_zz, part_zr, 1, ls.seq << 32, bseq, zz, zr, sh, s_bc);
+        double v[2];
+        v[0] = block_sum(zz, sh);
+        v[1] = block_sum(zr, sh);
+        const bool ok = pcg_sync<2>(a, v, 1, ls.seq << 32, epoch, sh, s_bc);
+        zz = v[0]; zr = v[1];
         if (threadIdx.x == 0) {
             step_after_setup(&ls, zz, zr);
             if (!ok) ls.reason = -101;
@@ -854,7 +910,10 @@ cg_persistent_kernel(const PcgArgs a)
             }
             if ((nloc & 1) && gtid == 0) a.p[nloc - 1] = first ? a.z[nloc - 1] : a.z[nloc - 1] + b * a.p[nloc - 1];
         }
-        grid.sync();
+        {
+            double none[1];
+            pcg_sync<0>(a, none, 0, 0ULL, epoch, sh, s_bc);
+        }
         // ---- halo push (nranks > 1): boundary values straight into the neighbours' ghost buffers ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 1u);
         if (a.multi) {
@@ -864,10 +923,10 @@ cg_persistent_kernel(const PcgArgs a)
             pushes++;
             if (threadIdx.x == 0) {
                 const unsigned int t = atomicAdd(a.push_ticket, 1u);
-                s_bc[3] = (t == gridDim.x * pushes - 1u) ? 1.0 : 0.0;
+                s_push = (t == gridDim.x * pushes - 1u) ? 1.0 : 0.0;
             }
             __syncthreads();
-            if (s_bc[3] != 0.0) {
+            if (s_push != 0.0) {
                 __threadfence_system();
                 if (threadIdx.x < a.ctx->nranks && a.ctx->sends_to[threadIdx.x])
                     st_release_sys(&a.ctx->mail[threadIdx.x]->halo_flag[a.ctx->rank], htag);
@@ -877,7 +936,10 @@ cg_persistent_kernel(const PcgArgs a)
         {
             double pw = 0.0;
             bool halo_ready = false, halo_ok = true;
-            for (int s = gwarp; s < a.nslices; s += gwarps) {
+            const int rot = a.has_off ? (a.nslices >> 1) : 0;
+            for (int s0 = gwarp; s0 < a.nslices; s0 += gwarps) {
+                int s = s0 + rot;
+                if (s >= a.nslices) s -= a.nslices;
                 const long long o0 = a.slice_off[s], o1 = a.slice_off[s + 1];
                 const int width = (int)((o1 - o0) >> 5);
                 const int *cp = a.scol + o0 + lane;
@@ -915,12 +977,11 @@ cg_persistent_kernel(const PcgArgs a)
                     pw = fma(a.p[r], sum, pw);
                 }
             }
-            pw = block_sum(pw, sh);
-            if (threadIdx.x == 0) part_pw[blockIdx.x] = halo_ok ? pw : __longlong_as_double(0x7ff8000000000000LL);
-            grid.sync();
-            double dummy;
-            const bool ok = pcg_reduce(a, part_pw, nullptr, 0, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 2u),
-                                       bseq, pw, dummy, sh, s_bc);
+            double v[1];
+            v[0] = block_sum(pw, sh);
+            if (!halo_ok) v[0] = __longlong_as_double(0x7ff8000000000000LL);
+            const bool ok = pcg_sync<1>(a, v, 0, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 2u), epoch, sh, s_bc);
+            pw = v[0];
             if (threadIdx.x == 0) {
                 step_after_spmv(&ls, pw);
                 if (!ok || pw != pw) ls.reason = -101;
@@ -952,17 +1013,205 @@ cg_persistent_kernel(const PcgArgs a)
                 a.x[i] = xv; a.r[i] = rv; a.z[i] = zv;
                 zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
             }
-            zz = block_sum(zz, sh);
-            zr = block_sum(zr, sh);
-            if (threadIdx.x == 0) { part_zz[blockIdx.x] = zz; part_zr[blockIdx.x] = zr; }
-            grid.sync();
-            const bool ok = pcg_reduce(a, part_zz, part_zr, 1, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 3u),
-                                       bseq, zz, zr, sh, s_bc);
+            double v[2];
+            v[0] = block_sum(zz, sh);
+            v[1] = block_sum(zr, sh);
+            const bool ok = pcg_sync<2>(a, v, 1, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 3u), epoch, sh, s_bc);
+            zz = v[0]; zr = v[1];
             if (threadIdx.x == 0) {
                 step_after_update(&ls, zz, zr);
                 if (!ok) ls.reason = -101;
             }
             __syncthreads();
+        }
+    }
+    if (gtid == 0) {
+        a.st->its = ls.its; a.st->reason = ls.reason; a.st->iter = ls.iter; a.st->dp = ls.dp;
+        a.st->beta = ls.beta; a.st->a = ls.a; a.st->b = ls.b;
+    }
+}
+
+
+// ---- single-reduction CG (PETSc's KSPCGUseSingleReduction / -ksp_cg_single_reduction recurrences) -----------------------
+// s = A z is formed instead of w = A p; w follows by recurrence (w = s + b w) and p.w by
+// dpi = delta - beta^2 dpiold / betaold^2 with delta = z.s, so ONE fused reduction (z.z, z.r, z.s) per iteration remains and
+// all vector updates collapse into one phase: two grid barriers and one cross-rank all-reduce per iteration.
+// Same iterates in exact arithmetic; selected for nranks > 1 where synchronisation, not bandwidth, bounds the iteration.
+
+__device__ void begin_iteration_sr(CgState *st)
+{
+    st->its = st->iter + 1;
+    if (st->beta == 0.0) { st->reason = PFEM_CONVERGED_ATOL; return; }
+    if (st->iter > 0 && st->beta * st->betaold < 0.0) { st->reason = PFEM_DIVERGED_INDEFINITE_PC; return; }
+    st->dpiold = st->dpi;
+    if (st->iter == 0) { st->b = 0.0; st->dpi = st->delta; }
+    else {
+        st->b = st->beta / st->betaold;
+        st->dpi = st->delta - st->beta * st->beta * st->dpiold / (st->betaold * st->betaold);
+    }
+    st->betaold = st->beta;
+    if (st->dpi == 0.0 || (st->iter > 0 && st->dpi * st->dpiold <= 0.0)) { st->reason = PFEM_DIVERGED_INDEFINITE_MAT; return; }
+    st->a = st->beta / st->dpi;
+}
+
+__device__ void step_sr(CgState *st, bool first, double zz, double zr, double zs)
+{
+    st->dp = sqrt(zz);
+    if (first) {
+        st->its = 0; st->iter = 0; st->dpi = 0.0; st->betaold = 0.0;
+        st->reason = converged_default(st, 0, st->dp);
+        if (st->reason) return;
+    } else {
+        st->reason = converged_default(st, st->iter + 1, st->dp);
+        if (st->reason) return;
+        st->iter++;
+        if (st->iter >= st->max_it) { st->reason = PFEM_DIVERGED_ITS; return; }
+    }
+    st->beta = zr;
+    st->delta = zs;
+    begin_iteration_sr(st);
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
+{
+    __shared__ double sh[64];
+    __shared__ double s_bc[4];
+    __shared__ double s_push;
+    __shared__ CgState ls;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    const int nloc = a.nloc;
+    unsigned long long epoch = 0;
+    unsigned int pushes = 0;
+    if (threadIdx.x == 0) {
+        ls.rtol = a.st->rtol; ls.abstol = a.st->abstol; ls.dtol = a.st->dtol; ls.max_it = a.st->max_it; ls.seq = a.st->seq;
+        ls.beta = ls.betaold = ls.dpi = ls.dpiold = ls.dp = ls.a = ls.b = ls.ttol = ls.rnorm0 = ls.delta = 0.0;
+        ls.its = 0; ls.reason = 0; ls.iter = 0;
+    }
+    __syncthreads();
+    // ---- set-up vectors: PCSetUp_Jacobi, x = 0, r = b, z = M^-1 r, p = w = 0 ----
+    for (int i = gtid; i < nloc; i += gthreads) {
+        double d = 0.0;
+        int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+        const int end = hi, c = a.row_lo + i;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (a.col[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo < end && a.col[lo] == c) d = a.val[lo];
+        const double di = a.pc_type == PFEM_PC_JACOBI ? (d == 0.0 ? 1.0 : 1.0 / d) : 1.0;
+        const double ri = a.b[i];
+        a.dinv[i] = di; a.x[i] = 0.0; a.r[i] = ri; a.z[i] = ri * di; a.p[i] = 0.0; a.w[i] = 0.0;
+    }
+    bool first = true;
+    unsigned int round = 0;
+    while (true) {
+        {
+            double none[1];
+            pcg_sync<0>(a, none, 0, 0ULL, epoch, sh, s_bc);
+        }
+        // ---- halo push of z (nranks > 1) ----
+        const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * round + 1u);
+        if (a.multi) {
+            for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], a.z[a.send_idx[i]]);
+            __threadfence_system();
+            __syncthreads();
+            pushes++;
+            if (threadIdx.x == 0) {
+                const unsigned int t = atomicAdd(a.push_ticket, 1u);
+                s_push = (t == gridDim.x * pushes - 1u) ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            if (s_push != 0.0) {
+                __threadfence_system();
+                if (threadIdx.x < a.ctx->nranks && a.ctx->sends_to[threadIdx.x])
+                    st_release_sys(&a.ctx->mail[threadIdx.x]->halo_flag[a.ctx->rank], htag);
+            }
+        }
+        // ---- s = A z, fused with (z.z, z.r, z.s) ----
+        double zz = 0.0, zr = 0.0, zs = 0.0;
+        bool halo_ready = false, halo_ok = true;
+        const int rot = a.has_off ? (a.nslices >> 1) : 0;
+        for (int s0 = gwarp; s0 < a.nslices; s0 += gwarps) {
+            int s = s0 + rot;
+            if (s >= a.nslices) s -= a.nslices;
+            const long long o0 = a.slice_off[s], o1 = a.slice_off[s + 1];
+            const int width = (int)((o1 - o0) >> 5);
+            const int *cp = a.scol + o0 + lane;
+            const double *vp = a.sval + o0 + lane;
+            double sum = 0.0;
+            int k = 0;
+            for (; k + 4 <= width; k += 4) {
+                const int c0 = __ldcs(cp + (k + 0) * 32), c1 = __ldcs(cp + (k + 1) * 32);
+                const int c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
+                const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32);
+                const double v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
+                const double x0 = a.z[c0], x1 = a.z[c1], x2 = a.z[c2], x3 = a.z[c3];
+                sum = fma(v0, x0, sum); sum = fma(v1, x1, sum); sum = fma(v2, x2, sum); sum = fma(v3, x3, sum);
+            }
+            for (; k < width; k++) sum = fma(__ldcs(vp + k * 32), a.z[__ldcs(cp + k * 32)], sum);
+            const int r = s * 32 + lane;
+            if (a.has_off) {
+                int lo = 0, hi = 0;
+                if (r < nloc) { lo = a.off_ptr[r]; hi = a.off_ptr[r + 1]; }
+                if (__any_sync(0xffffffffu, hi > lo)) {
+                    if (!halo_ready) {
+                        bool okw = true;
+                        if (lane < a.ctx->nranks && a.ctx->recvs_from[lane])
+                            okw = p2p_wait(&a.ctx->mail[a.ctx->rank]->halo_flag[lane], htag);
+                        halo_ok = __all_sync(0xffffffffu, okw);
+                        halo_ready = true;
+                    }
+                    double osum = 0.0;
+                    for (int q = lo; q < hi; q++) osum = fma(a.bval[q], __ldcg(a.ghost + a.bcol[q]), osum);
+                    sum = sum + osum;
+                }
+            }
+            if (r < nloc) {
+                sv[r] = sum;
+                const double zi = a.z[r], ri = a.r[r];
+                zz = fma(zi, zi, zz); zr = fma(zi, ri, zr); zs = fma(zi, sum, zs);
+            }
+        }
+        double v[3];
+        v[0] = block_sum(zz, sh);
+        v[1] = block_sum(zr, sh);
+        v[2] = block_sum(zs, sh);
+        if (!halo_ok) v[0] = __longlong_as_double(0x7ff8000000000000LL);
+        const bool ok = pcg_sync<3>(a, v, (int)(round & 1u), (ls.seq << 32) | (unsigned long long)(4u * round + 2u), epoch, sh, s_bc);   // mailbox parity: see p2p_allreduce
+        if (threadIdx.x == 0) {
+            step_sr(&ls, first, v[0], v[1], v[2]);
+            if (!ok || v[0] != v[0]) ls.reason = -101;
+        }
+        __syncthreads();
+        first = false;
+        round++;
+        if (ls.reason != 0) break;
+        // ---- all vector updates of the iteration in one pass ----
+        {
+            const double al = ls.a, b = ls.b;
+            const int n2 = nloc >> 1;
+            const double2 *s2 = reinterpret_cast<const double2 *>(sv), *d2 = reinterpret_cast<const double2 *>(a.dinv);
+            double2 *p2 = reinterpret_cast<double2 *>(a.p), *w2 = reinterpret_cast<double2 *>(a.w);
+            double2 *x2 = reinterpret_cast<double2 *>(a.x), *r2 = reinterpret_cast<double2 *>(a.r), *z2 = reinterpret_cast<double2 *>(a.z);
+            for (int i = gtid; i < n2; i += gthreads) {
+                const double2 zv = z2[i], svv = s2[i], dv = d2[i];
+                double2 pv = p2[i], wv = w2[i], xv = x2[i], rv = r2[i], zn;
+                pv.x = fma(b, pv.x, zv.x); pv.y = fma(b, pv.y, zv.y);            // p = z + b p
+                wv.x = fma(b, wv.x, svv.x); wv.y = fma(b, wv.y, svv.y);          // w = s + b w  (= A p)
+                xv.x = fma(al, pv.x, xv.x); xv.y = fma(al, pv.y, xv.y);
+                rv.x = fma(-al, wv.x, rv.x); rv.y = fma(-al, wv.y, rv.y);
+                zn.x = rv.x * dv.x; zn.y = rv.y * dv.y;
+                p2[i] = pv; w2[i] = wv; x2[i] = xv; r2[i] = rv; z2[i] = zn;
+            }
+            if ((nloc & 1) && gtid == 0) {
+                const int i = nloc - 1;
+                const double pv = fma(b, a.p[i], a.z[i]), wv = fma(b, a.w[i], sv[i]);
+                const double xv = fma(al, pv, a.x[i]), rv = fma(-al, wv, a.r[i]);
+                a.p[i] = pv; a.w[i] = wv; a.x[i] = xv; a.r[i] = rv; a.z[i] = rv * a.dinv[i];
+            }
         }
     }
     if (gtid == 0) {
@@ -981,15 +1230,27 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     int coop = 0;
     PFEM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     if (!coop) return PFEM_OK;
+    // CTA shape: many resident threads feed HBM best on big blocks (5 x 256 per SM); fewer, fatter CTAs make the grid
+    // barriers cheaper when the per-GPU block is small (1 x 1024 per SM = 148 arrivals)
+    const char *cfg = getenv("PFEM_PCG_CFG");
+    int threads = h->size_local >= 3000000 ? 256 : 1024, minb = h->size_local >= 3000000 ? 5 : 1;
+    if (cfg) sscanf(cfg, "%dx%d", &threads, &minb);
+    // recurrence: PETSc's default two-reduction CG on one rank, its single-reduction variant across ranks
+    const char *srenv = getenv("PFEM_CG_SR");
+    const bool sr = srenv ? (srenv[0] == '1') : (h->nranks > 1);
+    const void *fn = nullptr;
+    if (threads == 256 && minb == 5) fn = sr ? (const void *)cg_persistent_sr_kernel<256, 5> : (const void *)cg_persistent_kernel<256, 5>;
+    else if (threads == 1024 && minb == 1) fn = sr ? (const void *)cg_persistent_sr_kernel<1024, 1> : (const void *)cg_persistent_kernel<1024, 1>;
+    else if (threads == 640 && minb == 2) fn = sr ? (const void *)cg_persistent_sr_kernel<640, 2> : (const void *)cg_persistent_kernel<640, 2>;
+    else if (threads == 512 && minb == 2) fn = sr ? (const void *)cg_persistent_sr_kernel<512, 2> : (const void *)cg_persistent_kernel<512, 2>;
+    else { set_error("PFEM_PCG_CFG: unsupported shape %dx%d", threads, minb); return PFEM_ERR_ARG; }
     int per_sm = 0;
-    PFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel, CG_THREADS, 0));
-    if (per_sm < 1) return PFEM_OK;
-    if (per_sm > 8) per_sm = 8;
-    const int grid = h->sm_count * per_sm;
-    if (grid > h->sm_count * 16) return PFEM_OK;
+    PFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, threads, 0, 0));
+    if (per_sm < minb) return PFEM_OK;
+    const int grid = h->sm_count * minb;
     cudaStream_t s = h->stream;
-    if (!h->pcg_bcast.p) PFEM_TRY(h->pcg_bcast.alloc(8));
-    PFEM_CUDA(cudaMemsetAsync(h->pcg_bcast.p, 0, 8 * sizeof(double), s));
+    if (!h->pcg_bcast.p) PFEM_TRY(h->pcg_bcast.alloc(16));
+    PFEM_CUDA(cudaMemsetAsync(h->pcg_bcast.p, 0, 16 * sizeof(double), s));
     PcgArgs a;
     memset(&a, 0, sizeof a);
     a.nloc = h->size_local; a.nslices = h->A.nslices; a.row_lo = h->row_lo; a.pc_type = h->pc_type;
@@ -1003,9 +1264,11 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     a.send_idx = h->send_idx.p; a.send_dst = h->send_dst.p;
     a.bcast = h->pcg_bcast.p;
     a.bcast_flag = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 4);
-    a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 6);
-    void *params[] = {(void *)&a};
-    PFEM_CUDA(cudaLaunchCooperativeKernel((const void *)cg_persistent_kernel, dim3(grid), dim3(CG_THREADS), params, 0, s));
+    a.arrive = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 8);
+    a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 12);
+    double *svp = h->sv.p;
+    void *params[] = {(void *)&a, (void *)&svp};
+    PFEM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), params, 0, s));
     h->launches++;
     used = true;
     return PFEM_OK;

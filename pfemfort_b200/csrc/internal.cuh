@@ -56,7 +56,7 @@ template <typename T> struct DevBuf {
 
 // Device-resident CG scalar state (one per solver).  Kernels early-out when reason != 0.
 struct CgState {
-    double beta, betaold, dpi, dpiold, dp, a, b, ttol, rnorm0;
+    double beta, betaold, dpi, dpiold, dp, a, b, ttol, rnorm0, delta;
     double rtol, abstol, dtol;
     double red[4];          // reduction landing zone (local sums; all-reduced in place for nranks > 1)
     int its, reason, iter, max_it;
@@ -69,10 +69,10 @@ struct NcclApi;             // comm.cu
 
 // Peer-memory (NVLink) exchange area of one rank; every peer maps it through CUDA IPC and writes into it directly.
 constexpr int P2P_MAX_RANKS = 16;
+struct P2pSlot { double value; unsigned long long tag; };   // written with ONE 16-byte store: the tag validates the value
 struct P2pMail {
     unsigned long long halo_flag[P2P_MAX_RANKS];        // peer q: "my boundary values for tag t are in your ghost buffer"
-    unsigned long long red_flag[2][P2P_MAX_RANKS];      // [phase][peer]
-    double red_val[2][P2P_MAX_RANKS][2];                // [phase][peer][value]
+    P2pSlot red[2][P2P_MAX_RANKS][4];                   // [phase][peer][value index]
 };
 struct P2pCtx {
     int rank, nranks;
@@ -150,7 +150,7 @@ struct pfem_solver {
     std::vector<int> send_counts, recv_counts, send_displs, recv_displs;
     pfem::DevBuf<int> send_idx;            // local row indices to pack, grouped by destination rank
     pfem::DevBuf<double> send_buf, ghost_buf;
-    pfem::DevBuf<double> x, r, z, p, w, dinv;
+    pfem::DevBuf<double> x, r, z, p, w, dinv, sv;   // sv: s = A z of the single-reduction CG variant
     pfem::DevBuf<double> partials;         // [4][max_blocks]
     pfem::DevBuf<pfem::CgState> cg;
     pfem::CgState *cg_host = nullptr;      // pinned mirror
