@@ -765,8 +765,7 @@ struct PcgArgs {
     CgState *st;
     const P2pCtx *ctx;
     const int *send_idx; double *const *send_dst;
-    double *bcast;                         // [0..2] values, [3] ok flag
-    unsigned long long *bcast_flag;        // epoch of the last released barrier
+    double *bcast;                         // 4 PcgSlot {value, epoch}: [0..2] reduction results, [3] ok flag / release
     unsigned long long *arrive;            // monotonically increasing CTA arrival counter of the barriers
     unsigned int *push_ticket;             // monotonically increasing CTA arrival counter of the halo pushes
 };
@@ -786,23 +785,42 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 // counter; the LAST CTA to arrive sums all partials in a fixed order, all-reduces them across the ranks if needed
 // (one 16-byte NVLink store per value and peer), publishes the result and releases everybody through one flag.
 // One synchronisation per phase instead of "grid barrier, then reduce, then broadcast".  NV = 0: plain barrier.
+struct PcgSlot { double value; unsigned long long tag; };     // published with ONE 16-byte store: the tag validates the value
+
+__device__ __forceinline__ void st_slot_gpu(PcgSlot *p, double v, unsigned long long tag)
+{
+    asm volatile("st.global.relaxed.gpu.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_slot_gpu(const PcgSlot *p, double &v, unsigned long long &tag)
+{
+    long long bits;
+    asm volatile("ld.global.relaxed.gpu.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(p) : "memory");
+    v = __longlong_as_double(bits);
+}
+__device__ __forceinline__ unsigned long long atom_add_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old;
+    asm volatile("atom.add.release.gpu.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+
 template <int NV>
 __device__ __forceinline__ bool pcg_sync(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
                                          unsigned long long &epoch, double *sh, double *s_bc)
 {
     __shared__ int s_last;
+    PcgSlot *slots = reinterpret_cast<PcgSlot *>(a.bcast);     // [0..2] values, [3] ok/plain-barrier slot
     epoch++;
-    __syncthreads();                       // every thread's global writes of this phase precede thread 0's fence
+    __syncthreads();                       // every thread's global writes of this phase precede thread 0's release
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < NV; i++) a.partials[i * a.pstride + blockIdx.x] = v[i];
-        __threadfence();
-        const unsigned long long t = atomicAdd(a.arrive, 1ULL);
+        const unsigned long long t = atom_add_release_gpu(a.arrive, 1ULL);
         s_last = (t == (unsigned long long)gridDim.x * epoch - 1ULL) ? 1 : 0;
     }
     __syncthreads();
     if (s_last) {
-        __threadfence();
+        __threadfence();                   // acquire side of the arrivals
         double r[NV > 0 ? NV : 1];
         bool ok = true;
         if (NV > 0) {
@@ -816,23 +834,31 @@ __device__ __forceinline__ bool pcg_sync(const PcgArgs &a, double (&v)[NV > 0 ? 
             }
         }
         if (threadIdx.x == 0) {
+            __threadfence();               // everything the grid wrote in this phase is ordered before the publication
 #pragma unroll
-            for (int i = 0; i < NV; i++) { a.bcast[i] = r[i]; s_bc[i] = r[i]; }
-            a.bcast[3] = ok ? 1.0 : 0.0; s_bc[3] = ok ? 1.0 : 0.0;
-            __threadfence();
-            st_release_gpu(a.bcast_flag, epoch);
+            for (int i = 0; i < NV; i++) { st_slot_gpu(slots + i, r[i], epoch); s_bc[i] = r[i]; }
+            st_slot_gpu(slots + 3, ok ? 1.0 : 0.0, epoch);
+            s_bc[3] = ok ? 1.0 : 0.0;
         }
     } else if (threadIdx.x == 0) {
         const long long c0 = clock64();
         bool ok = true;
-        while (ld_acquire_gpu(a.bcast_flag) != epoch) {
+        double val;
+        unsigned long long tg;
+        ld_slot_gpu(slots + 3, val, tg);
+        while (tg != epoch) {              // relaxed polling: no cache maintenance inside the loop
             if (clock64() - c0 > 40000000000LL) { ok = false; break; }       // ~20 s
-            __nanosleep(40);               // keep the pollers off the L2 slice that has to deliver the release
+            __nanosleep(32);
+            ld_slot_gpu(slots + 3, val, tg);
         }
-        __threadfence();                   // gpu-scope fence: drops this SM's stale L1 lines before the next phase reads
+        s_bc[3] = ok ? val : 0.0;
 #pragma unroll
-        for (int i = 0; i < NV; i++) s_bc[i] = __ldcg(a.bcast + i);
-        s_bc[3] = ok ? __ldcg(a.bcast + 3) : 0.0;
+        for (int i = 0; i < NV; i++) {
+            ld_slot_gpu(slots + i, val, tg);
+            while (ok && tg != epoch) ld_slot_gpu(slots + i, val, tg);
+            s_bc[i] = val;
+        }
+        __threadfence();                   // one gpu-scope fence: acquire + drop this SM's stale L1 lines
     }
     __syncthreads();
 #pragma unroll
@@ -1263,7 +1289,6 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     a.partials = h->partials.p; a.st = h->cg.p; a.ctx = a.multi ? h->p2p_ctx.p : nullptr;
     a.send_idx = h->send_idx.p; a.send_dst = h->send_dst.p;
     a.bcast = h->pcg_bcast.p;
-    a.bcast_flag = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 4);
     a.arrive = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 8);
     a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 12);
     double *svp = h->sv.p;
