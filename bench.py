@@ -46,8 +46,8 @@ def parse():
     ap.add_argument("--partition", default="metis", choices=["metis", "slab"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-elems", type=int, default=6_000_000, help="elements in the CPU assembly sample")
-    ap.add_argument("--cpu-its", type=int, default=10, help="CG iterations in the CPU solve sample")
+    ap.add_argument("--cpu-elems", type=int, default=48_000_000, help="elements in the CPU assembly sample")
+    ap.add_argument("--cpu-its", type=int, default=100, help="CG iterations in the CPU solve sample")
     return ap.parse_args()
 
 

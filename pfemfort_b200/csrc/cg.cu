@@ -868,9 +868,13 @@ __device__ __forceinline__ bool pcg_sync(const PcgArgs &a, double (&v)[NV > 0 ? 
     return okall;
 }
 
-template <int THREADS, int MINB>
+// FUSED: the direction phase (p = z + b p) and its grid barrier are folded into the SpMV: every gathered entry is formed
+// on the fly as fma(b, p_old[c], z[c]) from the previous direction (p is double-buffered), the halo push forms its values
+// the same way, and the row's own entry is written out as the new direction.  Two barriers per iteration instead of three
+// at the price of a second gather stream (L2-resident once the rows are split over several GPUs).
+template <int THREADS, int MINB, bool FUSED>
 __global__ void __launch_bounds__(THREADS, MINB)
-cg_persistent_kernel(const PcgArgs a)
+cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
 {
     __shared__ double sh[64];
     __shared__ double s_bc[4];
@@ -921,8 +925,12 @@ cg_persistent_kernel(const PcgArgs a)
 
     while (ls.reason == 0) {
         // ---- direction: p = z + b p ----
-        {
-            const bool first = ls.iter == 0;
+        const bool first = ls.iter == 0;
+        const double bdir = ls.b;
+        double *p_new = a.p;
+        const double *p_old = a.p;
+        if (FUSED) { p_new = (ls.iter & 1) ? a.p : pbuf2; p_old = (ls.iter & 1) ? pbuf2 : a.p; }
+        if (!FUSED) {
             const double b = ls.b;
             const int n2 = nloc >> 1;
             const double2 *z2 = reinterpret_cast<const double2 *>(a.z);
@@ -935,15 +943,18 @@ cg_persistent_kernel(const PcgArgs a)
                 p2[i] = pv;
             }
             if ((nloc & 1) && gtid == 0) a.p[nloc - 1] = first ? a.z[nloc - 1] : a.z[nloc - 1] + b * a.p[nloc - 1];
-        }
-        {
             double none[1];
             pcg_sync<0>(a, none, 0, 0ULL, epoch, sh, s_bc);
         }
+        auto pval = [&](int c) -> double {     // entry c of the current direction
+            if (!FUSED) return a.p[c];
+            const double zc = a.z[c];
+            return first ? zc : fma(bdir, p_old[c], zc);
+        };
         // ---- halo push (nranks > 1): boundary values straight into the neighbours' ghost buffers ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 1u);
         if (a.multi) {
-            for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], a.p[a.send_idx[i]]);
+            for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], pval(a.send_idx[i]));
             __threadfence_system();
             __syncthreads();
             pushes++;
@@ -977,10 +988,10 @@ cg_persistent_kernel(const PcgArgs a)
                     const int c2 = __ldcs(cp + (k + 2) * 32), c3 = __ldcs(cp + (k + 3) * 32);
                     const double v0 = __ldcs(vp + (k + 0) * 32), v1 = __ldcs(vp + (k + 1) * 32);
                     const double v2 = __ldcs(vp + (k + 2) * 32), v3 = __ldcs(vp + (k + 3) * 32);
-                    const double x0 = a.p[c0], x1 = a.p[c1], x2 = a.p[c2], x3 = a.p[c3];
+                    const double x0 = pval(c0), x1 = pval(c1), x2 = pval(c2), x3 = pval(c3);
                     sum = fma(v0, x0, sum); sum = fma(v1, x1, sum); sum = fma(v2, x2, sum); sum = fma(v3, x3, sum);
                 }
-                for (; k < width; k++) sum = fma(__ldcs(vp + k * 32), a.p[__ldcs(cp + k * 32)], sum);
+                for (; k < width; k++) sum = fma(__ldcs(vp + k * 32), pval(__ldcs(cp + k * 32)), sum);
                 const int r = s * 32 + lane;
                 if (a.has_off) {
                     int lo = 0, hi = 0;
@@ -999,8 +1010,10 @@ cg_persistent_kernel(const PcgArgs a)
                     }
                 }
                 if (r < nloc) {
+                    const double pr = pval(r);
+                    if (FUSED) p_new[r] = pr;
                     a.w[r] = sum;
-                    pw = fma(a.p[r], sum, pw);
+                    pw = fma(pr, sum, pw);
                 }
             }
             double v[1];
@@ -1020,7 +1033,7 @@ cg_persistent_kernel(const PcgArgs a)
             const double al = ls.a;
             double zz = 0.0, zr = 0.0;
             const int n2 = nloc >> 1;
-            const double2 *p2 = reinterpret_cast<const double2 *>(a.p), *w2 = reinterpret_cast<const double2 *>(a.w);
+            const double2 *p2 = reinterpret_cast<const double2 *>(p_new), *w2 = reinterpret_cast<const double2 *>(a.w);
             const double2 *d2 = reinterpret_cast<const double2 *>(a.dinv);
             double2 *x2 = reinterpret_cast<double2 *>(a.x), *r2 = reinterpret_cast<double2 *>(a.r), *z2 = reinterpret_cast<double2 *>(a.z);
             for (int i = gtid; i < n2; i += gthreads) {
@@ -1035,7 +1048,7 @@ cg_persistent_kernel(const PcgArgs a)
             }
             if ((nloc & 1) && gtid == 0) {
                 const int i = nloc - 1;
-                const double xv = fma(al, a.p[i], a.x[i]), rv = fma(-al, a.w[i], a.r[i]), zv = rv * a.dinv[i];
+                const double xv = fma(al, p_new[i], a.x[i]), rv = fma(-al, a.w[i], a.r[i]), zv = rv * a.dinv[i];
                 a.x[i] = xv; a.r[i] = rv; a.z[i] = zv;
                 zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
             }
@@ -1261,15 +1274,24 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     const char *cfg = getenv("PFEM_PCG_CFG");
     int threads = h->size_local >= 3000000 ? 256 : 1024, minb = h->size_local >= 3000000 ? 5 : 1;
     if (cfg) sscanf(cfg, "%dx%d", &threads, &minb);
-    // recurrence: PETSc's default two-reduction CG on one rank, its single-reduction variant across ranks
+    // recurrence: PETSc's default two-reduction CG.  Its single-reduction variant (PFEM_CG_SR=1) saves one barrier and one
+    // all-reduce per iteration but moves one more vector; measured slower on 1 and 2 B200s (0.228 vs 0.211 ms/iteration on
+    // C5 at 2 GPUs), so it is opt-in.
     const char *srenv = getenv("PFEM_CG_SR");
-    const bool sr = srenv ? (srenv[0] == '1') : (h->nranks > 1);
+    const bool sr = srenv ? (srenv[0] == '1') : false;
     const void *fn = nullptr;
-    if (threads == 256 && minb == 5) fn = sr ? (const void *)cg_persistent_sr_kernel<256, 5> : (const void *)cg_persistent_kernel<256, 5>;
-    else if (threads == 1024 && minb == 1) fn = sr ? (const void *)cg_persistent_sr_kernel<1024, 1> : (const void *)cg_persistent_kernel<1024, 1>;
-    else if (threads == 640 && minb == 2) fn = sr ? (const void *)cg_persistent_sr_kernel<640, 2> : (const void *)cg_persistent_kernel<640, 2>;
-    else if (threads == 512 && minb == 2) fn = sr ? (const void *)cg_persistent_sr_kernel<512, 2> : (const void *)cg_persistent_kernel<512, 2>;
+    // optional: fold the direction phase into the SpMV (PFEM_PCG_FUSED=1).  Measured on 2 x B200 it is a wash (the
+    // cross-GPU latency chain, not the barrier count, bounds the iteration) and on one GPU the second gather stream costs
+    // 20 %, so it is off by default.
+    const char *fenv = getenv("PFEM_PCG_FUSED");
+    const bool fused = fenv ? (fenv[0] == '1') : false;
+#define PCG_PICK(T, M) (sr ? (const void *)cg_persistent_sr_kernel<T, M> : fused ? (const void *)cg_persistent_kernel<T, M, true> : (const void *)cg_persistent_kernel<T, M, false>)
+    if (threads == 256 && minb == 5) fn = PCG_PICK(256, 5);
+    else if (threads == 1024 && minb == 1) fn = PCG_PICK(1024, 1);
+    else if (threads == 640 && minb == 2) fn = PCG_PICK(640, 2);
+    else if (threads == 512 && minb == 2) fn = PCG_PICK(512, 2);
     else { set_error("PFEM_PCG_CFG: unsupported shape %dx%d", threads, minb); return PFEM_ERR_ARG; }
+#undef PCG_PICK
     int per_sm = 0;
     PFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, threads, 0, 0));
     if (per_sm < minb) return PFEM_OK;

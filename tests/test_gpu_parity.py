@@ -260,24 +260,26 @@ def test_persistent_and_multi_kernel_cg_agree(gpu, input_dir, monkeypatch):
         m, kind = _load(name, input_dir)
         num = D.number(m, kind)
         res = []
-        for mode, sr in (("persistent", "0"), ("kernels", "0"), ("persistent", "1")):
+        for mode, sr, fused in (("persistent", "0", "0"), ("kernels", "0", "0"), ("persistent", "1", "0"), ("persistent", "0", "1")):
             monkeypatch.setenv("PFEM_CG", mode)
-            monkeypatch.setenv("PFEM_CG_SR", sr)     # 1: PETSc's single-reduction recurrences (default for nranks > 1)
+            monkeypatch.setenv("PFEM_CG_SR", sr)     # 1: PETSc's single-reduction recurrences
+            monkeypatch.setenv("PFEM_PCG_FUSED", fused)   # 1: direction folded into the SpMV (default for nranks > 1)
             s = S.SolverB200(0)
             info = D.run_rank(s, m, num, rtol=1e-10)
             res.append((info["its"], info["reason"], s.get_solution()))
             s.free()
-        assert res[0][1] == res[1][1] == res[2][1] == 2
-        assert abs(res[0][0] - res[1][0]) <= 1
+        assert res[0][1] == res[1][1] == res[2][1] == res[3][1] == 2
+        assert abs(res[0][0] - res[1][0]) <= 1 and abs(res[3][0] - res[1][0]) <= 1
         assert abs(res[2][0] - res[1][0]) <= max(1, ITS_TOL * res[1][0])
-        for k in (0, 2):
+        for k in (0, 2, 3):
             assert np.abs(res[k][2] - res[1][2]).max() <= 1e-8 * np.abs(res[1][2]).max()
     # max_it reached -> DIVERGED_ITS (-3) with its = max_it, on both paths
     m, kind = _load("tet10", input_dir)
     num = D.number(m, kind)
-    for mode, sr in (("persistent", "0"), ("kernels", "0"), ("persistent", "1")):
+    for mode, sr, fused in (("persistent", "0", "0"), ("kernels", "0", "0"), ("persistent", "1", "0"), ("persistent", "0", "1")):
         monkeypatch.setenv("PFEM_CG", mode)
         monkeypatch.setenv("PFEM_CG_SR", sr)
+        monkeypatch.setenv("PFEM_PCG_FUSED", fused)
         s = S.SolverB200(0)
         info = D.run_rank(s, m, num, rtol=1e-10, max_it=7)
         assert (info["its"], info["reason"]) == (7, -3)
