@@ -43,6 +43,7 @@ def _digest(paths) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pfem_b200.h"),
+                                                               os.path.join(HERE, "..", "drivers", "pfem_driver.cpp"),
                                                                os.path.abspath(__file__)]
     stamp = os.path.join(OBJDIR, "stamp")
     dig = _digest(deps)
@@ -69,6 +70,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link failed")
+    # the C++ counterpart of the Fortran driver PROGRAMs, linked against the shared library only
+    os.makedirs(os.path.join(HERE, "bin"), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-o", os.path.join(HERE, "bin", "pfem_driver"),
+           os.path.join(HERE, "..", "drivers", "pfem_driver.cpp"), "-L" + HERE, "-lpfemb200", "-Wl,-rpath," + HERE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("driver link failed")
     with open(os.path.join(OBJDIR, "build.log"), "w") as f:
         f.write("\n".join(log))
     with open(stamp, "w") as f:

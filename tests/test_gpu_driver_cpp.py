@@ -1,0 +1,80 @@
+"""The C++ counterpart of the Fortran driver PROGRAMs (drivers/pfem_driver.cpp): same command line, same text input
+files, same temp.dat output; linked against libpfemb200.so only."""
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from pfemfort_b200 import driver as D, mesh as M, solver as S
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "pfemfort_b200", "bin", "pfem_driver")
+
+
+def _unpack(name, input_dir, tmp):
+    out = []
+    for part in ("nodes", "elems", "DirichBC", "ForceBC"):
+        src = os.path.join(input_dir, f"{name}-{part}.dat.gz")
+        if not os.path.exists(src):
+            continue
+        dst = os.path.join(tmp, f"{name}-{part}.dat")
+        with gzip.open(src, "rb") as f, open(dst, "wb") as g:
+            shutil.copyfileobj(f, g)
+        out.append(dst)
+    return out
+
+
+def _oracle_solution(m, kind, rtol):
+    num = D.number(m, kind)
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    rp, col = O.pattern(num.elemDof, num.size_global)
+    val, rhs, _ = O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied, D.DEFAULT_ELEMDATA[kind],
+                             D.DEFAULT_TIMEDATA, rp, col)
+    if m.fbc_node.size:
+        O.add_force_bc(rhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, num.node_map_get_new, num.NodeDofArrayNew, num.size_global)
+    x, its, reason, _ = O.cg_jacobi(rp, col, val, rhs, rtol=rtol)
+    return num, x, its
+
+
+@pytest.mark.parametrize("name,phys,kind", [("tet10", "tetrapoisson", S.POISSON_TETRA), ("tria20x20", "triapoisson", S.POISSON_TRIA),
+                                            ("cookmembranetria32", "triaelasticity", S.ELASTICITY_TRIA)])
+def test_cpp_driver_single_rank(gpu, input_dir, tmp_path, name, phys, kind):
+    files = _unpack(name, input_dir, str(tmp_path))
+    env = dict(os.environ, PFEM_KSP_RTOL="1e-10")
+    r = subprocess.run([DRIVER, phys] + files, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = M.read_mesh(os.path.join(input_dir, name))
+    num, ox, oits = _oracle_solution(m, kind, 1e-10)
+    assert f"Convergence in {oits} iterations." in r.stdout or f"Convergence in {oits + 1} iterations." in r.stdout \
+        or f"Convergence in {oits - 1} iterations." in r.stdout, r.stdout
+    t = np.loadtxt(os.path.join(str(tmp_path), "temp.dat"))
+    assert t.shape[0] == num.size_global
+    assert np.abs(t[:, 2] - ox).max() <= 1e-7 * np.abs(ox).max()
+    # the second column is the (old-numbering) node slot of every free dof, like assyForSoln
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    free = np.flatnonzero(num.NodeDofArrayNew.T.ravel() > 0) + 1
+    assert np.array_equal(t[:, 1].astype(int), free)
+
+
+def test_cpp_driver_two_ranks(gpu, input_dir, tmp_path):
+    if S.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    files = _unpack("tet10", input_dir, str(tmp_path))
+    env = dict(os.environ, PFEM_KSP_RTOL="1e-10", PFEM_NCCL_ID_FILE=os.path.join(str(tmp_path), "nccl.id"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", DRIVER, "tetrapoisson"] + files
+    r = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    m = M.read_mesh(os.path.join(input_dir, "tet10"))
+    t = np.loadtxt(os.path.join(str(tmp_path), "temp.dat"))
+    # temp.dat: (dof index in the partition-renumbered system, old node id, value): compare nodally with the exact solution
+    u = np.zeros(m.nNode)
+    u[t[:, 1].astype(int) - 1] = t[:, 2]
+    free = t[:, 1].astype(int) - 1
+    assert np.abs(u[free] - (m.coords[:, free] ** 2).sum(0)).max() < 2e-7
