@@ -2,6 +2,8 @@
 // interface each entry point replaces).  Host code only: argument checks, the PetscSolver state machine
 // (solverpetsc.F:64-68, 409-445, 498-509) and dispatch to the CUDA translation units.
 #include <cstdarg>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <new>
 
@@ -17,6 +19,23 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+}
+
+double StageTimer::now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+StageTimer::StageTimer(const char *n) : name(n), t0(0), on(false)
+{
+    const char *e = getenv("PFEM_TRACE");
+    on = e && e[0] == '1';
+    if (on) { cudaDeviceSynchronize(); t0 = now(); }
+}
+StageTimer::~StageTimer()
+{
+    if (on) { cudaDeviceSynchronize(); fprintf(stderr, "[pfem trace] %-28s %8.3f ms\n", name, 1e3 * (now() - t0)); }
 }
 
 static int need_handle(pfem_solver *h, const char *who)
@@ -204,7 +223,10 @@ int pfem_solver_set_pattern(pfem_solver_t *h, int nElem, int nsize, const int *e
 {
     PFEM_TRY(need_handle(h, "pfem_solver_set_pattern"));
     PFEM_TRY(build_pattern(h, nElem, nsize, elemDof));
-    PFEM_TRY(build_solver_structures(h));
+    {
+        StageTimer tm("pattern: solver structures");
+        PFEM_TRY(build_solver_structures(h));
+    }
     h->state = PFEM_PATTERN_OK;
     return PFEM_OK;
 }

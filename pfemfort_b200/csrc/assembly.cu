@@ -347,13 +347,40 @@ static int dispatch_rows(pfem_solver *h, const AsmArgs &args)
     return PFEM_ERR_SIZE;
 }
 
+// largest CSR / incidence segment over the R-row CTAs, for the four CTA shapes at once
+__global__ void segment_max_kernel(int nloc, const int *__restrict__ rowptr, const int *__restrict__ rinc_ptr, int *__restrict__ out)
+{
+    const int shapes[4] = {256, 128, 64, 32};
+    int mx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r0 = (blockIdx.x * blockDim.x + threadIdx.x) * 32; r0 < nloc; r0 += gridDim.x * blockDim.x * 32) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (r0 % shapes[q]) continue;
+            const int r1 = min(r0 + shapes[q], nloc);
+            mx[q] = max(mx[q], rowptr[r1] - rowptr[r0]);
+            mx[4 + q] = max(mx[4 + q], rinc_ptr[r1] - rinc_ptr[r0]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int v = mx[q];
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out + q, v);
+    }
+}
+
 // Pick the rows-per-CTA so that the largest CTA segment (CSR values + columns + incidences) fits in smem.
 int plan_assembly(pfem_solver *h)
 {
     const int nloc = h->size_local;
-    std::vector<int> rp((size_t)nloc + 1), ip((size_t)nloc + 1);
-    PFEM_CUDA(cudaMemcpy(rp.data(), h->rowptr.p, ((size_t)nloc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
-    PFEM_CUDA(cudaMemcpy(ip.data(), h->rinc_ptr.p, ((size_t)nloc + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    DevBuf<int> dmx;
+    PFEM_TRY(dmx.alloc(8));
+    PFEM_CUDA(cudaMemsetAsync(dmx.p, 0, 8 * sizeof(int), h->stream));
+    segment_max_kernel<<<h->sm_count * 4, 256, 0, h->stream>>>(nloc, h->rowptr.p, h->rinc_ptr.p, dmx.p);
+    h->launches++;
+    int mxs[8];
+    PFEM_CUDA(cudaMemcpyAsync(mxs, dmx.p, sizeof mxs, cudaMemcpyDeviceToHost, h->stream));
+    PFEM_CUDA(cudaStreamSynchronize(h->stream));
     int max_smem = 0;
     PFEM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     const int shapes[4] = {256, 128, 64, 32};
@@ -364,14 +391,11 @@ int plan_assembly(pfem_solver *h)
         const size_t limit = pass == 0 ? (size_t)max_smem / 2 - 1024 : (size_t)max_smem;
         for (int idx = 0; idx < 4; idx++) {
             // the streamed kernel is register-bound and barrier-free at one warp per CTA: prefer the smallest shape
-            const int R = h->asm_sell ? shapes[3 - idx] : shapes[idx];
+            const int q = h->asm_sell ? 3 - idx : idx;
+            const int R = shapes[q];
             if (forced && R != forced) continue;
-            int mn = 0, mi = 0;
-            for (int r0 = 0; r0 < nloc; r0 += R) {
-                const int r1 = r0 + R < nloc ? r0 + R : nloc;
-                mn = std::max(mn, rp[r1] - rp[r0]);
-                mi = std::max(mi, ip[r1] - ip[r0]);
-            }
+            int mn = mxs[q];
+            const int mi = mxs[4 + q];
             mn = (mn + 1) & ~1;   // keep the int arrays 8-byte aligned
             const size_t bytes = h->asm_sell ? (size_t)mn * 8 + 16 + (size_t)R * 8 : (size_t)mn * 12 + (size_t)mi * 4 + 16;
             if (bytes <= limit) {

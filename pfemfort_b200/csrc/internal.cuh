@@ -31,9 +31,12 @@ void set_error(const char *fmt, ...);
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    // Re-use the existing allocation when it is large enough (and not wastefully larger): repeated pattern passes
+    // (every end-to-end step) then cost no cudaMalloc/cudaFree round trips.  Contents are NOT cleared.
     int alloc(size_t count) {
-        release();
         if (count == 0) count = 1;
+        if (p && n >= count && n <= 2 * count + 4096) return PFEM_OK;
+        release();
         cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
         if (e != cudaSuccess) {
             p = nullptr;
@@ -134,6 +137,7 @@ struct pfem_solver {
     int asm_rows_per_cta = 0, asm_max_seg = 0;
     size_t asm_smem = 0;
     pfem::DevBuf<int> neg_count;
+    pfem::DevBuf<char> scratch[8];         // persistent set-up scratch (sort buffers, upload staging), re-used across calls
 
     // solver
     pfem::SellMatrix A;                    // diagonal block
@@ -208,5 +212,22 @@ int comm_p2p_setup(pfem_solver *h);
 void comm_p2p_teardown(pfem_solver *h, bool final);
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// typed view of one of the handle's persistent scratch buffers
+template <typename T> inline int scratch_get(pfem_solver *h, int idx, size_t count, T **out)
+{
+    int st = h->scratch[idx].alloc(count * sizeof(T) + 256);
+    if (st != PFEM_OK) return st;
+    *out = reinterpret_cast<T *>(h->scratch[idx].p);
+    return PFEM_OK;
+}
+
+// PFEM_TRACE=1: print host wall time of the set-up stages (stderr)
+struct StageTimer {
+    const char *name; double t0; bool on;
+    static double now();
+    explicit StageTimer(const char *n);
+    ~StageTimer();
+};
 
 }  // namespace pfem

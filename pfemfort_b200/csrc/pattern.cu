@@ -79,8 +79,8 @@ int upload_mesh(pfem_solver *h, int kind, int nElem, const int *conn, int nNode,
     PFEM_TRY(h->erec.alloc((size_t)nElem * h->rec_ints));
     PFEM_CUDA(cudaMemsetAsync(h->erec.p, 0xFF, (size_t)nElem * h->rec_ints * sizeof(int), s));
     {
-        DevBuf<int> tmp;
-        PFEM_TRY(tmp.alloc((size_t)nElem * npe));
+        struct { int *p; } tmp;
+        PFEM_TRY(scratch_get<int>(h, 1, (size_t)nElem * npe, &tmp.p));
         PFEM_CUDA(cudaMemcpyAsync(tmp.p, conn, (size_t)nElem * npe * sizeof(int), cudaMemcpyHostToDevice, s));
         DevBuf<int> bad;
         PFEM_TRY(bad.alloc(1));
@@ -95,12 +95,13 @@ int upload_mesh(pfem_solver *h, int kind, int nElem, const int *conn, int nNode,
     }
     {
         const int stride = ndim == 3 ? 4 : 2;
-        DevBuf<double> tmp;
-        DevBuf<int> map;
-        PFEM_TRY(tmp.alloc((size_t)nNode * ndim));
+        struct { double *p; } tmp;
+        struct { int *p; } map;
+        map.p = nullptr;
+        PFEM_TRY(scratch_get<double>(h, 2, (size_t)nNode * ndim, &tmp.p));
         PFEM_CUDA(cudaMemcpyAsync(tmp.p, coords, (size_t)nNode * ndim * sizeof(double), cudaMemcpyHostToDevice, s));
         if (node_map_get_old) {
-            PFEM_TRY(map.alloc(nNode));
+            PFEM_TRY(scratch_get<int>(h, 3, (size_t)nNode, &map.p));
             PFEM_CUDA(cudaMemcpyAsync(map.p, node_map_get_old, (size_t)nNode * sizeof(int), cudaMemcpyHostToDevice, s));
             DevBuf<int> bad;
             PFEM_TRY(bad.alloc(1));
@@ -343,13 +344,15 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
     const long long total = (long long)nElem * nsize;
     // 1. element dof records
     {
-        DevBuf<int> tmp, bad;
-        PFEM_TRY(tmp.alloc((size_t)total));
+        StageTimer tm("pattern: upload+pack dofs");
+        DevBuf<int> bad;
+        int *tmp = nullptr;
+        PFEM_TRY(scratch_get<int>(h, 0, (size_t)total, &tmp));
         PFEM_TRY(bad.alloc(1));
-        PFEM_CUDA(cudaMemcpyAsync(tmp.p, elemDof, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s));
+        PFEM_CUDA(cudaMemcpyAsync(tmp, elemDof, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, s));
         PFEM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
-        check_range_kernel<<<G, 256, 0, s>>>(total, tmp.p, -1, h->size_global, bad.p);
-        pack_dof_kernel<<<G, 256, 0, s>>>(nElem, h->npe, nsize, h->rec_ints, tmp.p, h->erec.p);
+        check_range_kernel<<<G, 256, 0, s>>>(total, tmp, -1, h->size_global, bad.p);
+        pack_dof_kernel<<<G, 256, 0, s>>>(nElem, h->npe, nsize, h->rec_ints, tmp, h->erec.p);
         h->launches += 2;
         int nbad = 0;
         PFEM_CUDA(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -360,20 +363,21 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
     // 2. row -> incidence lists: stable radix sort of (local row, e*nsize+k); ties keep ascending code order
     PFEM_TRY(h->rinc_ptr.alloc((size_t)nloc + 1));
     {
-        DevBuf<int> k_in, k_out, v_in, v_out;
-        PFEM_TRY(k_in.alloc((size_t)total));
-        PFEM_TRY(k_out.alloc((size_t)total));
-        PFEM_TRY(v_in.alloc((size_t)total));
-        PFEM_TRY(v_out.alloc((size_t)total));
+        StageTimer tm("pattern: incidence sort");
+        struct { int *p; } k_in, k_out, v_in, v_out;
+        PFEM_TRY(scratch_get<int>(h, 0, (size_t)total, &k_in.p));
+        PFEM_TRY(scratch_get<int>(h, 1, (size_t)total, &k_out.p));
+        PFEM_TRY(scratch_get<int>(h, 2, (size_t)total, &v_in.p));
+        PFEM_TRY(scratch_get<int>(h, 3, (size_t)total, &v_out.p));
         inc_keys_kernel<<<G, 256, 0, s>>>(total, nsize, h->npe, h->rec_ints, h->erec.p, h->row_lo, h->row_hi, k_in.p, v_in.p);
         h->launches++;
         int bits = 1;
         while ((1LL << bits) <= nloc) bits++;
         size_t tmp_bytes = 0;
         PFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, total, 0, bits, s));
-        DevBuf<char> tmp;
-        PFEM_TRY(tmp.alloc(tmp_bytes));
-        PFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, total, 0, bits, s));
+        char *tmp = nullptr;
+        PFEM_TRY(scratch_get<char>(h, 4, tmp_bytes, &tmp));
+        PFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, total, 0, bits, s));
         lower_bound_kernel<<<G, 256, 0, s>>>(nloc, total, k_out.p, h->rinc_ptr.p);
         h->launches += 2;
         int ninc = 0;
@@ -386,6 +390,7 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
     }
     // 3. pattern: per-row sorted unique columns
     {
+        StageTimer tm("pattern: row unique + csr");
         DevBuf<long long> cand, cand_off;
         DevBuf<int> rowlen;
         PFEM_TRY(cand.alloc((size_t)nloc + 1));
@@ -406,8 +411,8 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
         long long ncand = 0;
         PFEM_CUDA(cudaMemcpyAsync(&ncand, cand_off.p + nloc, sizeof(long long), cudaMemcpyDeviceToHost, s));
         PFEM_CUDA(cudaStreamSynchronize(s));
-        DevBuf<int> scratch;
-        PFEM_TRY(scratch.alloc((size_t)ncand));
+        struct { int *p; } scratch;
+        PFEM_TRY(scratch_get<int>(h, 5, (size_t)ncand, &scratch.p));
         row_unique_kernel<<<G, 128, 0, s>>>(nloc, nsize, h->npe, h->rec_ints, h->erec.p, h->rinc_ptr.p, h->rinc.p,
                                             cand_off.p, scratch.p, rowlen.p);
         h->launches++;
@@ -437,9 +442,15 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
     h->values_zero = true;
     h->rhs_zero = true;
     PFEM_TRY(h->neg_count.alloc(1));
-    PFEM_TRY(build_asm_streams(h));
+    {
+        StageTimer tm("pattern: value-pass streams");
+        PFEM_TRY(build_asm_streams(h));
+    }
     h->asm_rows_per_cta = 0;
-    PFEM_TRY(plan_assembly(h));
+    {
+        StageTimer tm("pattern: plan assembly");
+        PFEM_TRY(plan_assembly(h));
+    }
     return PFEM_OK;
 }
 
