@@ -253,10 +253,11 @@ def main():
         conn, edof, node_map = num.conn_new, num.elemDof, None
     # pinned host staging of the step inputs (the e2e leg copies from these every step)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    conn_p, edof_p, coords_p, applied_p = pin(conn), pin(edof), pin(m.coords), pin(num.solnApplied)
+    conn_p, coords_p, applied_p = pin(conn), pin(m.coords), pin(num.solnApplied)
     map_p = pin(node_map) if node_map is not None else None
+    nda_p = pin(num.NodeDofArrayNew)
     xout_p = torch.empty(num.size_global, dtype=torch.float64).pin_memory().numpy()
-    h2d_bytes = conn_p.nbytes + edof_p.nbytes + coords_p.nbytes + applied_p.nbytes + (map_p.nbytes if map_p is not None else 0)
+    h2d_bytes = conn_p.nbytes + nda_p.nbytes + coords_p.nbytes + applied_p.nbytes + (map_p.nbytes if map_p is not None else 0)
     d2h_bytes = xout_p.nbytes
 
     s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
@@ -273,7 +274,7 @@ def main():
         s.initialise(size_local, num.size_global)
         s.set_options(rtol=RTOL, max_it=100000, pc_type=S.PC_JACOBI)
         timed("set_mesh", s.set_mesh, kind, conn_p, coords_p, map_p)
-        timed("set_pattern", s.set_pattern, edof_p)
+        timed("set_pattern", s.set_pattern_nodal, nda_p)     # element dof lists are formed on the GPU
         timed("set_applied", s.set_applied, applied_p)
 
     def hot_step():

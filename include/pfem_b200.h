@@ -111,6 +111,11 @@ int pfem_solver_set_mesh(pfem_solver_t *h, int kind, int nElem, const int *conn,
  * (sorted unique global columns, explicit zeros kept, negative dofs dropped) and the row -> element
  * incidence lists the value pass gathers from.  State -> PFEM_PATTERN_OK. */
 int pfem_solver_set_pattern(pfem_solver_t *h, int nElem, int nsize, const int *elemDof);
+/* Same pattern pass, but the element dof lists are formed on the GPU from the nodal numbering:
+ * ElemDofArray(e, ndof*(i-1)+j) = NodeDofArrayNew(conn(e,i), j) - 1 (tetrapoissonparallelimpl1.F:698-713).
+ * NodeDofArrayNew is the driver's array (column-major nNode x ndof, 1-based dof id, 0 = Dirichlet); the host then
+ * uploads nNode*ndof ints instead of nElem*nsize. */
+int pfem_solver_set_pattern_nodal(pfem_solver_t *h, int ndof, const int *NodeDofArrayNew);
 /* PetscSolver%setZero, solverpetsc.F:222-246 */
 int pfem_solver_set_zero(pfem_solver_t *h);
 /* solnApplied (tetrapoissonparallelimpl1.F:352,676): applied Dirichlet values indexed (node-1)*ndof+dof, NEW ids */

@@ -219,10 +219,24 @@ int pfem_solver_set_mesh(pfem_solver_t *h, int kind, int nElem, const int *conn,
     return upload_mesh(h, kind, nElem, conn, nNode, coords, node_map_get_old);
 }
 
+int pfem_solver_set_pattern_nodal(pfem_solver_t *h, int ndof, const int *NodeDofArrayNew)
+{
+    PFEM_TRY(need_handle(h, "pfem_solver_set_pattern_nodal"));
+    if (!h->have_mesh) { set_error("pfem_solver_set_pattern_nodal: call pfem_solver_set_mesh first"); return PFEM_ERR_STATE; }
+    if (ndof != h->ndof || !NodeDofArrayNew) { set_error("pfem_solver_set_pattern_nodal: bad argument"); return PFEM_ERR_ARG; }
+    PFEM_TRY(build_pattern(h, h->nElem, h->nsize, nullptr, NodeDofArrayNew));
+    {
+        StageTimer tm("pattern: solver structures");
+        PFEM_TRY(build_solver_structures(h));
+    }
+    h->state = PFEM_PATTERN_OK;
+    return PFEM_OK;
+}
+
 int pfem_solver_set_pattern(pfem_solver_t *h, int nElem, int nsize, const int *elemDof)
 {
     PFEM_TRY(need_handle(h, "pfem_solver_set_pattern"));
-    PFEM_TRY(build_pattern(h, nElem, nsize, elemDof));
+    PFEM_TRY(build_pattern(h, nElem, nsize, elemDof, nullptr));
     {
         StageTimer tm("pattern: solver structures");
         PFEM_TRY(build_solver_structures(h));

@@ -46,6 +46,14 @@ template <typename T> struct DevBuf {
         n = count;
         return PFEM_OK;
     }
+    // grow-only variant for scratch space: never shrinks, so alternating uses of different sizes do not thrash
+    // (a cudaFree + cudaMalloc pair of ~1 GB costs ~100 ms of page mapping work)
+    int reserve(size_t count) {
+        if (count == 0) count = 1;
+        if (p && n >= count) return PFEM_OK;
+        release();
+        return alloc(count);
+    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -188,7 +196,7 @@ int element_ke_batch(int kind, int n, const double *x, const double *y, const do
 // pattern.cu
 int upload_mesh(pfem_solver *h, int kind, int nElem, const int *conn, int nNode, const double *coords,
                 const int *node_map_get_old);
-int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof);
+int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof, const int *nodeDof);
 // assembly.cu
 int plan_assembly(pfem_solver *h);
 int assemble_values(pfem_solver *h, const double *elemData, const double *timeData, int *n_neg);
@@ -216,7 +224,7 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // typed view of one of the handle's persistent scratch buffers
 template <typename T> inline int scratch_get(pfem_solver *h, int idx, size_t count, T **out)
 {
-    int st = h->scratch[idx].alloc(count * sizeof(T) + 256);
+    int st = h->scratch[idx].reserve(count * sizeof(T) + 256);
     if (st != PFEM_OK) return st;
     *out = reinterpret_cast<T *>(h->scratch[idx].p);
     return PFEM_OK;

@@ -330,11 +330,24 @@ static int build_asm_streams(pfem_solver *h)
     return PFEM_OK;
 }
 
-int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
+// ElemDofArray(e, ndof*(i-1)+j) = NodeDofArrayNew(conn(e,i), j) - 1   (tetrapoissonparallelimpl1.F:698-713), on the GPU
+__global__ void nodal_dof_kernel(int nElem, int npe, int ndof, int nNode, int rec_ints, const int *__restrict__ nda,
+                                 int *__restrict__ erec)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)nElem * npe;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(t / npe), i = (int)(t - (long long)e * npe);
+        int *rec = erec + (size_t)e * rec_ints;
+        const int node = rec[i];
+        for (int d = 0; d < ndof; d++) rec[npe + ndof * i + d] = nda[(size_t)d * nNode + node] - 1;
+    }
+}
+
+int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof, const int *nodeDof)
 {
     if (!h->initialised) { set_error("pfem_solver_set_pattern: call pfem_solver_initialise first"); return PFEM_ERR_STATE; }
     if (!h->have_mesh) { set_error("pfem_solver_set_pattern: call pfem_solver_set_mesh first"); return PFEM_ERR_STATE; }
-    if (nElem != h->nElem || nsize != h->nsize || !elemDof) {
+    if (nElem != h->nElem || nsize != h->nsize || (!elemDof && !nodeDof)) {
         set_error("pfem_solver_set_pattern: nElem/nsize (%d,%d) do not match the mesh (%d,%d)", nElem, nsize, h->nElem, h->nsize);
         return PFEM_ERR_ARG;
     }
@@ -343,7 +356,23 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof)
     const int nloc = h->size_local;
     const long long total = (long long)nElem * nsize;
     // 1. element dof records
-    {
+    if (!elemDof) {
+        StageTimer tm("pattern: nodal dofs -> element records");
+        DevBuf<int> bad;
+        int *tmp = nullptr;
+        const size_t nn = (size_t)h->nNode * h->ndof;
+        PFEM_TRY(scratch_get<int>(h, 0, nn, &tmp));
+        PFEM_TRY(bad.alloc(1));
+        PFEM_CUDA(cudaMemcpyAsync(tmp, nodeDof, nn * sizeof(int), cudaMemcpyHostToDevice, s));
+        PFEM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+        check_range_kernel<<<G, 256, 0, s>>>((long long)nn, tmp, 0, h->size_global + 1, bad.p);
+        nodal_dof_kernel<<<G, 256, 0, s>>>(nElem, h->npe, h->ndof, h->nNode, h->rec_ints, tmp, h->erec.p);
+        h->launches += 2;
+        int nbad = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        if (nbad) { set_error("pfem_solver_set_pattern_nodal: %d dof ids outside 0..size_global", nbad); return PFEM_ERR_NUMBERING; }
+    } else {
         StageTimer tm("pattern: upload+pack dofs");
         DevBuf<int> bad;
         int *tmp = nullptr;

@@ -197,6 +197,10 @@ class SolverB200:
         ed = _i32(elemDof)
         _chk(self._lib.pfem_solver_set_pattern(self._h, ed.shape[1], ed.shape[0], _ptr(ed, C.c_int)))
 
+    def set_pattern_nodal(self, NodeDofArrayNew):
+        nda = _i32(NodeDofArrayNew)              # [ndof, nNode] = column-major nNode x ndof
+        _chk(self._lib.pfem_solver_set_pattern_nodal(self._h, nda.shape[0], _ptr(nda, C.c_int)))
+
     def set_applied(self, solnApplied):
         sa = _f64(solnApplied)
         _chk(self._lib.pfem_solver_set_applied(self._h, _ptr(sa, C.c_double), sa.size))

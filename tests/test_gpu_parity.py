@@ -284,3 +284,26 @@ def test_persistent_and_multi_kernel_cg_agree(gpu, input_dir, monkeypatch):
         info = D.run_rank(s, m, num, rtol=1e-10, max_it=7)
         assert (info["its"], info["reason"]) == (7, -3)
         s.free()
+
+
+def test_nodal_pattern_pass_equals_element_dof_pattern_pass(gpu, input_dir):
+    """pfem_solver_set_pattern_nodal forms ElemDofArray on the GPU (tetrapoissonparallelimpl1.F:698-713)."""
+    for name in ("tet10", "beam3Dtet6366", "cookmembranetria32"):
+        m, kind = _load(name, input_dir)
+        num = D.number(m, kind)
+        out = []
+        for nodal in (False, True):
+            s = S.SolverB200(0)
+            s.initialise(num.size_global, num.size_global)
+            s.set_mesh(kind, num.conn_new, m.coords)
+            if nodal:
+                s.set_pattern_nodal(num.NodeDofArrayNew)
+            else:
+                s.set_pattern(num.elemDof)
+            s.setZero()
+            s.set_applied(num.solnApplied)
+            s.assemble(D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA)
+            out.append(s.get_csr() + (s.get_rhs(),))
+            s.free()
+        for a, b in zip(out[0], out[1]):
+            assert np.array_equal(a, b)
