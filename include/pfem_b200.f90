@@ -51,6 +51,11 @@
           INTEGER(C_INT), VALUE :: nElem, nsize
           INTEGER(C_INT) :: elemDof(nElem,*)                        ! ElemDofArray(nElem,nsize)
         END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_solver_set_pattern_nodal(h, ndof, NodeDofArrayNew) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: h
+          INTEGER(C_INT), VALUE :: ndof
+          INTEGER(C_INT) :: NodeDofArrayNew(*)                      ! NodeDofArrayNew(nNode,ndof)
+        END FUNCTION
         INTEGER(C_INT) FUNCTION pfem_solver_set_zero(h) BIND(C)
           IMPORT; TYPE(C_PTR), VALUE :: h
         END FUNCTION

@@ -216,6 +216,7 @@ int pfem_solver_set_mesh(pfem_solver_t *h, int kind, int nElem, const int *conn,
                          const int *node_map_get_old)
 {
     PFEM_TRY(need_handle(h, "pfem_solver_set_mesh"));
+    h->state = PFEM_SOLVER_EMPTY;        // a new mesh invalidates the pattern: the pattern pass must run again
     return upload_mesh(h, kind, nElem, conn, nNode, coords, node_map_get_old);
 }
 

@@ -160,3 +160,33 @@ def test_generators_against_the_large_reference_files():
     assert np.array_equal(g.dbc_node, ref[:, 0].astype(np.int32)) and np.array_equal(g.dbc_val, ref[:, 2])
     nodes = np.loadtxt(gzip.open("/root/reference/input/tria1000x1000-nodes.dat.gz", "rt"))
     assert np.array_equal(g.coords, nodes[:, 1:].T)
+
+
+def test_force_bc_rows_host_logic_matches_oracle(input_dir):
+    """driver.force_bc_rows (host side of the ForceBC loop, tetraelasticityparallelimpl1.F:971-982) against the oracle,
+    with the reference's row formula and with the corrected index."""
+    for name, kind, swap in (("beam3Dtet6366", S.ELASTICITY_TETRA, True), ("cookmembranetria32", S.ELASTICITY_TRIA, False)):
+        m = M.read_mesh(os.path.join(input_dir, name), swap_34=swap)
+        npe, ndof, ndim = S.KIND_DIMS[kind]
+        num = D.number(m, kind)
+        for fix in (False, True):
+            rhs = np.zeros(num.size_global)
+            O.add_force_bc(rhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, num.node_map_get_new, num.NodeDofArrayNew, num.size_global, fix=fix)
+            mine = np.zeros(num.size_global)
+            rows, vals = D.force_bc_rows(m, num, ndof, fix)
+            for r, v in zip(rows, vals):
+                mine[r] += v
+            assert np.array_equal(rhs, mine)
+
+
+def test_nodal_solution_scatter(input_dir):
+    m = M.read_mesh(os.path.join(input_dir, "tet10"))
+    _, npart = D.partition(m, S.POISSON_TETRA, 3)
+    num = D.number(m, S.POISSON_TETRA, 3, npart)
+    x = np.arange(1, num.size_global + 1, dtype=np.float64)
+    u = D.nodal_solution(num, x)[0]
+    dbc = dict(zip(m.dbc_node, m.dbc_val))
+    for old in range(1, m.nNode + 1, 37):
+        new = num.node_map_get_new[old - 1]
+        dof = num.NodeDofArrayNew[0, new - 1]
+        assert u[old - 1] == (x[dof - 1] if dof > 0 else dbc[old])
