@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(R) assemble_sell_kernel(const AsmArgs a)
         int4 c0 = load_conn(e0), c1 = load_conn(e1);
         double xq[NPE], yq[NPE], zq[NPE];                  // coordinates of the element of the NEXT iteration
         load_xyz(c0, xq, yq, zq);
+#pragma unroll 2      // two copies: the coordinate / node-id register sets ping-pong instead of being copied (unroll 6: slower)
         for (int m = 0; m < width; m++) {
             const Ent e3 = load_entry(m + 3);
             const int4 c2 = load_conn(e2);
