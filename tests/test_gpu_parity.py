@@ -307,3 +307,78 @@ def test_nodal_pattern_pass_equals_element_dof_pattern_pass(gpu, input_dir):
             s.free()
         for a, b in zip(out[0], out[1]):
             assert np.array_equal(a, b)
+
+
+def _check_against_oracle(m, kind, num=None, rtol=1e-10):
+    num = num or D.number(m, kind)
+    s = S.SolverB200(0)
+    info = D.run_rank(s, m, num, rtol=rtol)
+    rp, col, val = s.get_csr()
+    rhs = s.get_rhs()
+    x = s.get_solution()
+    s.free()
+    orp, ocol, oval, orhs = _oracle_system(m, kind, num)
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+    assert np.array_equal(val, oval) and np.array_equal(rhs, orhs)
+    ox, oits, oreason, _ = O.cg_jacobi(orp, ocol, oval, orhs, rtol=rtol)
+    assert info["reason"] == oreason
+    assert abs(info["its"] - oits) <= max(1, ITS_TOL * oits)
+    assert np.abs(x - ox).max() <= 1e-6 * max(np.abs(ox).max(), 1e-300)
+    return num, x
+
+
+def test_nonzero_and_partial_dirichlet_elasticity(gpu, input_dir):
+    """Lifting with ndof > 1: non-zero applied displacements, and nodes where only SOME dofs are constrained
+    (tetraelasticityparallelimpl1.F:938-958 indexes solnApplied by (node-1)*ndof+dof)."""
+    m, kind = _load("beam3Dtet6366", input_dir)
+    m.fbc_node = m.fbc_node[:0]; m.fbc_dof = m.fbc_dof[:0]; m.fbc_val = m.fbc_val[:0]
+    top = np.flatnonzero(np.abs(m.coords[1] - m.coords[1].max()) < 1e-9) + 1          # y = 6 face
+    m.dbc_node = np.concatenate([m.dbc_node, top, top[::2]]).astype(np.int32)
+    m.dbc_dof = np.concatenate([m.dbc_dof, np.full(top.size, 2), np.full(top[::2].size, 1)]).astype(np.int32)   # uy everywhere, ux on every other node
+    m.dbc_val = np.concatenate([m.dbc_val, np.full(top.size, 0.05), 0.01 * np.arange(top[::2].size)])
+    _check_against_oracle(m, kind)
+    m2, kind2 = _load("cookmembranetria32", input_dir)
+    right = np.flatnonzero(np.abs(m2.coords[0] - m2.coords[0].max()) < 1e-9) + 1
+    m2.dbc_node = np.concatenate([m2.dbc_node, right]).astype(np.int32)
+    m2.dbc_dof = np.concatenate([m2.dbc_dof, np.full(right.size, 2)]).astype(np.int32)
+    m2.dbc_val = np.concatenate([m2.dbc_val, np.linspace(0.1, 0.3, right.size)])
+    _check_against_oracle(m2, kind2)
+
+
+def test_randomly_renumbered_mesh(gpu, input_dir):
+    """Unstructured numbering: nodes and elements of tet10 / cookmembrane randomly permuted (wide, irregular rows, no
+    locality).  The solution must be the permuted solution of the original mesh."""
+    rng = np.random.default_rng(2024)
+    for name in ("tet10", "cookmembranetria32"):
+        m, kind = _load(name, input_dir)
+        npe, ndof, ndim = S.KIND_DIMS[kind]
+        perm = rng.permutation(m.nNode)                 # new position of old node n is inv[n]
+        inv = np.empty(m.nNode, np.int64)
+        inv[perm] = np.arange(m.nNode)
+        eperm = rng.permutation(m.nElem)
+        m2 = M.Mesh(np.ascontiguousarray(m.coords[:, perm]), np.ascontiguousarray((inv[m.conn - 1] + 1)[:, eperm]).astype(np.int32),
+                    (inv[m.dbc_node - 1] + 1).astype(np.int32), m.dbc_dof.copy(), m.dbc_val.copy(),
+                    (inv[m.fbc_node - 1] + 1).astype(np.int32) if m.fbc_node.size else m.fbc_node, m.fbc_dof, m.fbc_val, name + "-perm")
+        num2, x2 = _check_against_oracle(m2, kind, rtol=1e-12)
+        if m.fbc_node.size:
+            continue        # the reference's node-based ForceBC row formula is numbering dependent by construction
+        num1 = D.number(m, kind)
+        s = S.SolverB200(0)
+        D.run_rank(s, m, num1, rtol=1e-12)
+        u1 = D.nodal_solution(num1, s.get_solution())
+        s.free()
+        u2 = D.nodal_solution(num2, x2)
+        assert np.abs(u2[:, inv] - u1).max() <= 1e-8 * np.abs(u1).max()
+
+
+def test_element_with_no_free_dof_and_single_element_mesh(gpu):
+    # one triangle, two Dirichlet nodes: a 1 x 1 system
+    coords = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    m = M.Mesh(coords, np.array([[1], [2], [3]], np.int32), np.array([1, 2], np.int32), np.array([1, 1], np.int32), np.array([2.0, -1.0]))
+    num, x = _check_against_oracle(m, S.POISSON_TRIA)
+    assert num.size_global == 1
+    # two triangles, the second one entirely on the Dirichlet boundary (no free dof): it must be ignored, not crash
+    coords = np.array([[0.0, 1.0, 0.0, 1.0], [0.0, 0.0, 1.0, 1.0]])
+    m = M.Mesh(coords, np.array([[1, 2], [2, 4], [3, 3]], np.int32), np.array([2, 3, 4], np.int32), np.ones(3, np.int32), np.array([1.0, 2.0, 3.0]))
+    num, x = _check_against_oracle(m, S.POISSON_TRIA)
+    assert num.size_global == 1
