@@ -382,3 +382,49 @@ def test_element_with_no_free_dof_and_single_element_mesh(gpu):
     m = M.Mesh(coords, np.array([[1, 2], [2, 4], [3, 3]], np.int32), np.array([2, 3, 4], np.int32), np.ones(3, np.int32), np.array([1.0, 2.0, 3.0]))
     num, x = _check_against_oracle(m, S.POISSON_TRIA)
     assert num.size_global == 1
+
+
+def test_petscsolver_assemble_mirrors(gpu, input_dir):
+    """PetscSolver%assembleMatrix / assembleVector / assembleMatrixAndVector (solverpetsc.F:328-401): entry
+    (R(ii), C(jj)) += KLOCAL(ii,jj), i.e. NOT transposed, unlike the drivers' direct MatSetValues."""
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    s.initialise(num.size_global, num.size_global)
+    s.set_mesh(kind, num.conn_new, m.coords)
+    s.set_pattern(num.elemDof)
+    s.setZero()
+    rng = np.random.default_rng(3)
+    rp, col, _ = s.get_csr()
+    ref_val = np.zeros(col.size)
+    ref_rhs = np.zeros(num.size_global)
+
+    def ref_add(r, c, v):
+        if r < 0 or c < 0:
+            return
+        k = rp[r] + np.searchsorted(col[rp[r]:rp[r + 1]], c)
+        ref_val[k] += v
+
+    for e in (0, 17, 4321, 5999):
+        dofs = num.elemDof[:, e]
+        K = rng.standard_normal((4, 4))
+        F = rng.standard_normal(4)
+        if e % 2:
+            s.assembleMatrix(dofs, dofs, K)
+            s.assembleVector(dofs, F)
+        else:
+            s.assembleMatrixAndVector(dofs, dofs, K, F)
+        for i in range(4):
+            if dofs[i] >= 0:
+                ref_rhs[dofs[i]] += F[i]
+            for j in range(4):
+                ref_add(dofs[i], dofs[j], K[i, j])
+    _, _, val = s.get_csr()
+    assert np.array_equal(val, ref_val) and np.array_equal(s.get_rhs(), ref_rhs)
+    # ForceBC-style single adds, negative / foreign rows ignored
+    s.add_value(5, 1.5)
+    s.add_value(-1, 9.0)
+    ref_rhs[5] += 1.5
+    assert np.array_equal(s.get_rhs(), ref_rhs)
+    assert s.launch_count() > 0 and s.time_spmv(3) > 0.0
+    s.free()

@@ -190,3 +190,18 @@ def test_nodal_solution_scatter(input_dir):
         new = num.node_map_get_new[old - 1]
         dof = num.NodeDofArrayNew[0, new - 1]
         assert u[old - 1] == (x[dof - 1] if dof > 0 else dbc[old])
+
+
+def test_oracle_cg_against_a_direct_solve(input_dir):
+    """The oracle's Jacobi-CG (PETSc semantics) converges to the solution of a sparse direct solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    for name, kind, swap in (("tet10", S.POISSON_TETRA, False), ("beam3Dtet6366", S.ELASTICITY_TETRA, True)):
+        m = M.read_mesh(os.path.join(input_dir, name), swap_34=swap)
+        o, edof, rp, col, val, rhs, _ = _system(m, kind)
+        A = sp.csr_matrix((val, col, rp), shape=(rp.size - 1, rp.size - 1))
+        assert abs(A - A.T).max() <= 1e-12 * abs(A).max()          # symmetric to rounding (Klocal is read transposed)
+        xd = spla.spsolve(A.tocsc(), rhs)
+        x, its, reason, rnorm = O.cg_jacobi(rp, col, val, rhs, rtol=1e-12, max_it=20000)
+        assert reason == 2
+        assert np.abs(x - xd).max() <= 1e-8 * np.abs(xd).max()
