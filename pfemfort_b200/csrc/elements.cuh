@@ -230,26 +230,26 @@ template <> struct ElemOp<ELASTICITY_TRIA> {
     Geom<3, 2> g; double dvol; double DB[3];
     __device__ __forceinline__ void load_geom(const double x[3], const double y[3], const double *) { tria_geom(x, y, g); }
     __device__ __forceinline__ void set_dvol(const Params<ELASTICITY_TRIA> &p) { dvol = p.gw * (g.Jac * p.thick); } // elasticity2D.F:94
-    // column b of MATMUL(Dmat, Bmat): inner index ascending, zeros included (:136)
+    // Column b of MATMUL(Dmat, Bmat) and entry (a,b) of MATMUL(BmatTrans, .) (:136-139).  The reference sums the inner
+    // index in ascending order with the structural zeros of Bmat/Dmat included; a zero term is an exact +-0 and leaves the
+    // running sum unchanged, so only the structurally non-zero terms are formed here, in the same ascending order: the
+    // results are bit-identical (up to the sign of an exact zero).
     __device__ __forceinline__ void col_setup(const Params<ELASTICITY_TRIA> &p, int b) {
         const int j = b >> 1, d = b & 1;
         const double dx = pick(g.dN[0], j), dy = pick(g.dN[1], j);
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int t = 0; t < 3; t++) acc = acc + p.D[s][t] * bmat2(t, d, dx, dy);
-            DB[s] = acc;
-        }
+        const double gd = d == 0 ? dx : dy;                       // the only non-zero of Bmat(0:1, b)
+        DB[0] = (d == 0 ? p.D[0][0] : p.D[0][1]) * gd;
+        DB[1] = (d == 0 ? p.D[1][0] : p.D[1][1]) * gd;
+        DB[2] = p.D[2][2] * (d == 0 ? dy : dx);
     }
     // Klocal(a,b) = dvol * sum_s Bmat(s,a) * DB(s,b)  (:138-139)
     __device__ __forceinline__ double K(const Params<ELASTICITY_TRIA> &, int a) const {
         const int i = a >> 1, d = a & 1;
         const double dx = pick(g.dN[0], i), dy = pick(g.dN[1], i);
-        double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < 3; s++) acc = acc + bmat2(s, d, dx, dy) * DB[s];
-        return dvol * acc;
+        // d = 0: rows xx (s=0) and xy (s=2); d = 1: rows yy (s=1) and xy (s=2)
+        const double t1 = (d == 0 ? dx : dy) * (d == 0 ? DB[0] : DB[1]);
+        const double t2 = (d == 0 ? dy : dx) * DB[2];
+        return dvol * (t1 + t2);
     }
     __device__ __forceinline__ void col_setup_unit(int) {}
     __device__ __forceinline__ double K_unit(int) const { return 0.0; }
@@ -266,24 +266,25 @@ template <> struct ElemOp<ELASTICITY_TETRA> {
     Geom<4, 3> g; double dvol; double DB[6];
     __device__ __forceinline__ void load_geom(const double x[4], const double y[4], const double z[4]) { tet_geom(x, y, z, g); }
     __device__ __forceinline__ void set_dvol(const Params<ELASTICITY_TETRA> &p) { dvol = p.gw * g.Jac; }            // elasticity3D.F:324
+    // see the 2-D operator: only the structurally non-zero terms of the two MATMULs, in the reference's ascending order
     __device__ __forceinline__ void col_setup(const Params<ELASTICITY_TETRA> &p, int b) {                            // :374
         const int j = b / 3, d = b - 3 * j;
         const double dx = pick(g.dN[0], j), dy = pick(g.dN[1], j), dz = pick(g.dN[2], j);
+        const double gd = d == 0 ? dx : (d == 1 ? dy : dz);       // the only non-zero of Bmat(0:2, b)
 #pragma unroll
-        for (int s = 0; s < 6; s++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int t = 0; t < 6; t++) acc = acc + p.D[s][t] * bmat3(t, d, dx, dy, dz);
-            DB[s] = acc;
-        }
+        for (int s = 0; s < 3; s++) DB[s] = (d == 0 ? p.D[s][0] : (d == 1 ? p.D[s][1] : p.D[s][2])) * gd;
+        DB[3] = p.D[3][3] * (d == 0 ? dy : (d == 1 ? dx : 0.0));  // xy
+        DB[4] = p.D[4][4] * (d == 1 ? dz : (d == 2 ? dy : 0.0));  // yz
+        DB[5] = p.D[5][5] * (d == 0 ? dz : (d == 2 ? dx : 0.0));  // zx
     }
     __device__ __forceinline__ double K(const Params<ELASTICITY_TETRA> &, int a) const {                             // :376-377
         const int i = a / 3, d = a - 3 * i;
         const double dx = pick(g.dN[0], i), dy = pick(g.dN[1], i), dz = pick(g.dN[2], i);
-        double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < 6; s++) acc = acc + bmat3(s, d, dx, dy, dz) * DB[s];
-        return dvol * acc;
+        // non-zero rows of Bmat(:, a), ascending: d=0: xx(0), xy(3), zx(5); d=1: yy(1), xy(3), yz(4); d=2: zz(2), yz(4), zx(5)
+        const double t1 = (d == 0 ? dx : (d == 1 ? dy : dz)) * (d == 0 ? DB[0] : (d == 1 ? DB[1] : DB[2]));
+        const double t2 = (d == 0 ? dy : (d == 1 ? dx : dy)) * (d == 2 ? DB[4] : DB[3]);
+        const double t3 = (d == 2 ? dx : dz) * (d == 1 ? DB[4] : DB[5]);
+        return dvol * ((t1 + t2) + t3);
     }
     __device__ __forceinline__ void col_setup_unit(int) {}
     __device__ __forceinline__ double K_unit(int) const { return 0.0; }
