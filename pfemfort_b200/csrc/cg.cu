@@ -1401,7 +1401,10 @@ int cg_solve(pfem_solver *h)
         return PFEM_OK;
     }
     const int gv = grid_for(h, nloc, 2);
-    const bool p2p = multi && h->p2p;
+    // launch-per-phase path: NCCL exchange by default; its peer-memory variant (the stepping stone towards the persistent
+    // kernel) only on request
+    const char *kp = getenv("PFEM_KERNELS_P2P");
+    const bool p2p = multi && h->p2p && kp && kp[0] == '1';
     const P2pCtx *ctx = p2p ? h->p2p_ctx.p : nullptr;
     cg_setup_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->row_lo, h->pc_type, h->rowptr.p, h->col.p, h->val.p, h->rhs.p, h->x.p,
                                               h->r.p, h->z.p, h->dinv.p, h->partials.p, pstride, h->cg.p,
