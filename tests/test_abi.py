@@ -53,3 +53,25 @@ def test_product_does_not_link_or_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "pyoracle" not in src and "liborc" not in src and "orc_" not in src, f
+
+
+def test_cpp_driver_fails_loudly_without_a_gpu(tmp_path):
+    """The compiled C++ driver links against libpfemb200.so only and refuses to run without a device."""
+    import gzip
+    import shutil
+    import subprocess
+    if S.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    drv = os.path.join(ROOT, "pfemfort_b200", "bin", "pfem_driver")
+    assert os.path.exists(drv), "run __graft_entry__.build()"
+    out = subprocess.run(["ldd", drv], capture_output=True, text=True).stdout
+    assert "libpfemb200.so" in out and "liborc" not in out
+    files = []
+    for part in ("nodes", "elems", "DirichBC"):
+        dst = os.path.join(str(tmp_path), f"tet10-{part}.dat")
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "input", f"tet10-{part}.dat.gz"), "rb") as f, open(dst, "wb") as g:
+            shutil.copyfileobj(f, g)
+        files.append(dst)
+    r = subprocess.run([drv, "tetrapoisson"] + files, cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+    assert "Total DOF = 729" in r.stdout          # the host side (reading, numbering) ran before the GPU was needed
