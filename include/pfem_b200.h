@@ -167,6 +167,10 @@ int pfem_solver_get_info(pfem_solver_t *h, int *its, int *reason, double *rnorm,
 int pfem_solver_get_state(pfem_solver_t *h, int *state, int *row_start, int *row_end, int *size_global);
 /* exchange path in use for nranks > 1: 0 = single rank, 1 = NCCL send/recv + all-reduce, 2 = peer-memory kernels (NVLink, CUDA IPC) */
 int pfem_solver_comm_mode(pfem_solver_t *h, int *mode);
+/* kernel used by the last value pass: 0 = generic row gather (binary-search slots), 1 = streamed row gather (default),
+ * 2 = tiled compute-once kernel (opt-in, PFEM_ASM=tiled, Poisson kinds); for mode 2 also the number of row tiles and the
+ * mean number of times an element is computed (1.0 = every element exactly once; the row gather computes a tet 4 times) */
+int pfem_solver_assembly_mode(pfem_solver_t *h, int *mode, int *ntiles, double *visits_per_element);
 /* kernel launches issued on this handle since the last call with reset != 0 */
 int pfem_solver_launch_count(pfem_solver_t *h, long long *launches, int reset);
 /* Run the CG SpMV (w = A p on an internal vector) `reps` times and report the mean device time per

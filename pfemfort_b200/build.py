@@ -20,8 +20,10 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 # element arithmetic must not be contracted into FMAs (bit-faithful to the reference's evaluation order)
-NO_FMA = {"elements.cu", "assembly.cu"}
-SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "cg.cu", "comm.cu", "host_driver.cu"]
+NO_FMA = {"elements.cu", "assembly.cu", "assembly_tiled.cu"}
+# host-side set-up loops (tile construction) use OpenMP
+OPENMP = {"assembly_tiled.cu"}
+SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "cg.cu", "comm.cu", "host_driver.cu"]
 
 
 def _nvcc() -> str:
@@ -57,13 +59,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc, *ARCH, *COMMON, "-c", os.path.join(CSRC, src), "-o", obj]
         if src in NO_FMA:
             cmd.insert(1, "-fmad=false")
+        if src in OPENMP:
+            cmd[1:1] = ["-Xcompiler", "-fopenmp"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             sys.stderr.write(log[-1])
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xlinker", "--exclude-libs,ALL", "-ldl",
+    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xlinker", "--exclude-libs,ALL", "-ldl", "-Xcompiler", "-fopenmp",
            "-L/usr/local/cuda/targets/x86_64-linux/lib", "-lmetis_static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)

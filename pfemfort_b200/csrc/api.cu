@@ -438,6 +438,16 @@ int pfem_solver_comm_mode(pfem_solver_t *h, int *mode)
     return PFEM_OK;
 }
 
+int pfem_solver_assembly_mode(pfem_solver_t *h, int *mode, int *ntiles, double *visits_per_element)
+{
+    if (!h) { set_error("NULL handle"); return PFEM_ERR_ARG; }
+    if (mode) *mode = h->last_asm_mode;
+    if (ntiles) *ntiles = h->last_asm_mode == 2 ? h->ntiles : 0;
+    if (visits_per_element)
+        *visits_per_element = (h->last_asm_mode == 2 && h->tile_elems_touched) ? (double)h->tile_elem_visits / (double)h->tile_elems_touched : 0.0;
+    return PFEM_OK;
+}
+
 int pfem_solver_launch_count(pfem_solver_t *h, long long *launches, int reset)
 {
     if (!h) { set_error("NULL handle"); return PFEM_ERR_ARG; }

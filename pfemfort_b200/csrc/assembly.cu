@@ -11,6 +11,7 @@
 // summed in exactly the order of the reference's sequential np=1 run, so the result is deterministic and,
 // because the TU is built with -fmad=false, bit-identical to the no-FMA CPU evaluation.
 #include <cstdlib>
+#include <cstring>
 
 #include "elements.cuh"
 #include "internal.cuh"
@@ -435,9 +436,15 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     a.max_seg_nnz = h->asm_max_seg;
     a.ainc_off = h->ainc_off.p; a.ainc = h->ainc.p; a.conn4 = h->conn4.p; a.neg_flag = h->neg_count.p;
     a.unit = (td[1] == 1.0 && ed[0] == 1.0 && ed[1] == 1.0 && (h->kind == PFEM_POISSON_TRIA || ed[2] == 1.0)) ? 1 : 0;
+    // opt-in: the tiled (compute-once) kernel for the one-dof-per-node kinds; tiles are built once per pattern
+    const char *mode = getenv("PFEM_ASM");
+    const bool want_tiled = mode && !strcmp(mode, "tiled") && h->ndof == 1;
+    if (want_tiled && !h->tiles_ready) PFEM_TRY(build_tiles_device(h));
     PFEM_CUDA(cudaEventRecord(h->ev0, s));
     int st = PFEM_OK;
-    switch (h->kind) {
+    h->last_asm_mode = (want_tiled && h->asm_tiled) ? 2 : (h->asm_sell ? 1 : 0);
+    if (want_tiled && h->asm_tiled) st = assemble_values_tiled(h, dED.p, dTD.p, a.unit != 0);
+    else switch (h->kind) {
     case PFEM_POISSON_TRIA: st = dispatch_rows<POISSON_TRIA>(h, a); break;
     case PFEM_POISSON_TETRA: st = dispatch_rows<POISSON_TETRA>(h, a); break;
     case PFEM_ELASTICITY_TRIA: st = dispatch_rows<ELASTICITY_TRIA>(h, a); break;

@@ -1,0 +1,242 @@
+// assembly_tiled.cuh -- the tiled (compute-once) value pass kernel for the one-dof-per-node kinds (Poisson tria/tet).
+//
+// Same job as assemble_sell_kernel (assembly.cu): the element loop of tetrapoissonparallelimpl1.F:828-884 /
+// triapoissonparallelimpl1.F:849-905 with PETSc's MatSetValues/VecSetValues(ADD) behind it, fused, without atomics,
+// summing every matrix entry in ascending element id (the reference's sequential np=1 order) with the no-FMA
+// arithmetic of elements.cuh => bit-identical to the row-gather kernel and to the CPU oracle.
+//
+// What changes is WHO computes an element.  The row-gather kernel recomputes the geometry of an element once per
+// incident row (4x for a tet) and is FP64-pipe/issue bound at ~22 % of the HBM roof.  Here a CTA owns a tile of
+// spatially close rows (tiles.hpp) and
+//   phase A: its threads compute each element that touches the tile ONCE and stage the columns Klocal(:,k) and the
+//            lifted Flocal(k) of the tile's own local dofs k in shared memory;
+//   phase B: one thread per tile row walks the row's incidence stream (coalesced {staged column, slot bytes}
+//            entries, ascending element id) and adds the staged column into the row's FP64 accumulators in shared
+//            memory at the precomputed slots (Dirichlet columns go to a sink: branch-free), and Flocal into the RHS;
+//   phase C: the accumulators are streamed to the CSR value array, one warp per row.
+//
+// This header is also compiled for the host by tests/emu (PFEM_EMULATE + a small CUDA shim), so it uses no warp
+// intrinsics; inline PTX is confined to tiled_ld_xyz.
+#pragma once
+#include "elements.cuh"
+#include "tiles.hpp"
+
+namespace pfem {
+
+struct TiledArgs {
+    const int *tdesc;                 // [ntiles][TILE_DESC_INTS]
+    const int2 *trows;                // { local row or -1, accumulator offset }
+    const int2 *tel;                  // { e | dbc<<31, base | mask<<24 }
+    const long long *tslice_off;
+    const int2 *tinc;                 // { staged column or -1, slot bytes }
+    const int4 *conn4;                // [nElem] 0-based NEW node ids
+    const int *erec;                  // [nElem][rec_ints] conn + dofs (Dirichlet elements only)
+    int rec_ints;
+    const double *xyz, *applied;
+    const int *rowptr;
+    double *val, *rhs;
+    const double *elemData, *timeData;
+    int *neg_flag;
+    int load_val, load_rhs;
+};
+
+// 256-bit read-only load of one node's (x, y, z, pad)
+__device__ __forceinline__ void tiled_ld_xyz(const double *p, double &x, double &y, double &z)
+{
+#if defined(__CUDA_ARCH__)
+    double w;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+#else
+    x = p[0]; y = p[1]; z = p[2];
+#endif
+}
+
+__device__ __forceinline__ double tiled_kcoef(const Params<POISSON_TRIA> &p, int d) { return d == 0 ? p.kx : p.ky; }
+__device__ __forceinline__ double tiled_kcoef(const Params<POISSON_TETRA> &p, int d) { return d == 0 ? p.kx : (d == 1 ? p.ky : p.kz); }
+
+#ifndef PFEM_DYN_SMEM
+#define PFEM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+template <int KIND, int THREADS, int MINB, bool UNIT>
+__global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const TiledArgs a)
+{
+    using T = ElemTraits<KIND>;
+    constexpr int NPE = T::NPE, NDIM = T::NDIM, NSIZE = NPE;
+    static_assert(T::NDOF == 1, "tiled value pass: one dof per node");
+    constexpr int NWARPS = THREADS / 32;
+
+    PFEM_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int *td = a.tdesc + (size_t)blockIdx.x * TILE_DESC_INTS;
+    const int row_off = td[TD_ROW_OFF], nrows_pad = td[TD_NROWS_PAD], el_off = td[TD_EL_OFF], nel = td[TD_NEL];
+    const int slice0 = td[TD_SLICE0], nnz = td[TD_NNZ], ncols = td[TD_NCOLS];
+    double *Kst = reinterpret_cast<double *>(smem_raw);      // [ncols][4]: Klocal(0..NSIZE-1, k) of a staged column
+    double *Fst = Kst + (size_t)ncols * 4;                   // [ncols]   : lifted Flocal(k)
+    double *acc = Fst + ncols;                               // [nnz]     : the tile's CSR values, tile-row order
+    double *sink = acc + nnz;                                // [THREADS] : Dirichlet columns land here (never used)
+
+    // ---- accumulators: zero, or the current values when the matrix was not zeroed since the last pass ----
+    sink[tid] = 0.0;
+    if (!a.load_val) {
+        for (int q = tid; q < nnz; q += THREADS) acc[q] = 0.0;
+    } else {
+        for (int i = warp; i < nrows_pad; i += NWARPS) {
+            const int2 tr = __ldg(a.trows + row_off + i);
+            if (tr.x < 0) continue;
+            const int c0 = a.rowptr[tr.x], len = a.rowptr[tr.x + 1] - c0;
+            for (int j = lane; j < len; j += 32) acc[tr.y + j] = a.val[c0 + j];
+        }
+    }
+
+    // ---- phase A: every element of the tile once ----
+    {
+        Params<KIND> prm;
+        prm.init(a.elemData, a.timeData);
+        const int2 *tel = a.tel + el_off;
+        auto load_te = [&](int i) { return i < nel ? __ldcs(tel + i) : make_int2(0, 0); };
+        auto load_conn = [&](const int2 &te) { return __ldg(a.conn4 + (te.x & 0x7fffffff)); };   // element 0 past the end
+        auto load_xyz = [&](const int4 &c, double (&x)[NPE], double (&y)[NPE], double (&z)[NPE]) {
+            const int nd[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < NPE; i++) {
+                if (NDIM == 3) tiled_ld_xyz(a.xyz + (size_t)nd[i] * 4, x[i], y[i], z[i]);
+                else {
+                    const double2 t = __ldg(reinterpret_cast<const double2 *>(a.xyz + (size_t)nd[i] * 2));
+                    x[i] = t.x; y[i] = t.y; z[i] = 0.0;
+                }
+            }
+        };
+        // software pipeline: tile entries three iterations ahead, node ids two ahead, next coordinates in flight
+        int2 te0 = load_te(tid), te1 = load_te(tid + THREADS), te2 = load_te(tid + 2 * THREADS);
+        int4 c0 = load_conn(te0), c1 = load_conn(te1);
+        double xq[NPE], yq[NPE], zq[NPE];
+        load_xyz(c0, xq, yq, zq);
+        for (int i = tid; i < nel; i += THREADS) {
+            const int2 te3 = load_te(i + 3 * THREADS);
+            const int4 c2 = load_conn(te2);
+            double x[NPE], y[NPE], z[NPE];
+#pragma unroll
+            for (int q = 0; q < NPE; q++) { x[q] = xq[q]; y[q] = yq[q]; z[q] = zq[q]; }
+            load_xyz(c1, xq, yq, zq);                          // next element: in flight during this one's arithmetic
+            const int2 te = te0;
+            const int4 cn = c0;
+            te0 = te1; te1 = te2; te2 = te3; c0 = c1; c1 = c2;
+
+            const int e = te.x & 0x7fffffff;
+            const unsigned int mask = ((unsigned int)te.y >> 24) & 15u;
+            int col = te.y & 0xffffff;
+            ElemOp<KIND> op;
+            op.load_geom(x, y, z);
+            const bool neg = op.g.Jac < 0.0;                   // the reference STOPs here: flag it, stage zeros
+            if (neg) atomicOr(a.neg_flag, 1);
+            op.set_dvol(prm);
+            // b_d(j) = dN_d(j) * dvol (poisson.F:87-89,177-179): shared by every column of the element
+            double bd[NDIM][NPE];
+#pragma unroll
+            for (int d = 0; d < NDIM; d++)
+#pragma unroll
+                for (int j = 0; j < NPE; j++) bd[d][j] = op.g.dN[d][j] * op.dvol;
+            // Dirichlet data of the element (rare): which local dofs are fixed, and their applied values
+            bool fixed[NSIZE];
+            double gval[NSIZE];
+#pragma unroll
+            for (int j = 0; j < NSIZE; j++) { fixed[j] = false; gval[j] = 0.0; }
+            if (te.x < 0) {
+                const int nd[4] = {cn.x, cn.y, cn.z, cn.w};
+                const int *dof = a.erec + (size_t)e * a.rec_ints + NPE;
+#pragma unroll
+                for (int j = 0; j < NSIZE; j++) {
+                    fixed[j] = dof[j] == -1;
+                    if (fixed[j]) gval[j] = a.applied[nd[j]];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NSIZE; k++) {
+                if (!((mask >> k) & 1u)) continue;
+                // MatSetValues(ADD) reads the column-major block row-major: entry (row k, col j) += Klocal(j, k),
+                // Klocal(j,k) = af*(b1(j)*(kx*dNx(k)) + b2(j)*(ky*dNy(k)) [+ b3(j)*(kz*dNz(k))])   (poisson.F:93-95,183-187)
+                double pk[NDIM];
+#pragma unroll
+                for (int d = 0; d < NDIM; d++) pk[d] = UNIT ? op.g.dN[d][k] : tiled_kcoef(prm, d) * op.g.dN[d][k];
+                double kc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int j = 0; j < NSIZE; j++) {
+                    double s = bd[0][j] * pk[0] + bd[1][j] * pk[1];
+                    if (NDIM == 3) s = s + bd[NDIM - 1][j] * pk[NDIM - 1];
+                    kc[j] = UNIT ? s : prm.af * s;
+                }
+                // Flocal(k) with valC = 0, then lifting in ascending Dirichlet local index: F_k -= Klocal(k, ii) * g_ii
+                double f = (op.g.N[k] * op.dvol) * prm.force;
+                if (te.x < 0) {
+#pragma unroll
+                    for (int ii = 0; ii < NSIZE; ii++) {
+                        if (!fixed[ii]) continue;
+                        double s = bd[0][k] * (tiled_kcoef(prm, 0) * op.g.dN[0][ii]) + bd[1][k] * (tiled_kcoef(prm, 1) * op.g.dN[1][ii]);
+                        if (NDIM == 3) s = s + bd[NDIM - 1][k] * (tiled_kcoef(prm, NDIM - 1) * op.g.dN[NDIM - 1][ii]);
+                        f = f - (prm.af * s) * gval[ii];
+                    }
+                }
+                if (neg) { kc[0] = kc[1] = kc[2] = kc[3] = 0.0; f = 0.0; }
+                double2 *dst = reinterpret_cast<double2 *>(Kst + (size_t)col * 4);
+                dst[0] = make_double2(kc[0], kc[1]);
+                dst[1] = make_double2(kc[2], kc[3]);
+                Fst[col] = f;
+                col++;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: one thread per tile row gathers its staged columns in ascending element id ----
+    if (tid < nrows_pad) {
+        const int2 tr = __ldg(a.trows + row_off + tid);
+        const bool live = tr.x >= 0;
+        double *racc = acc + tr.y;
+        double *dummy = sink + tid;
+        double facc = (live && a.load_rhs) ? a.rhs[tr.x] : 0.0;
+        const long long o0 = a.tslice_off[slice0 + warp];
+        const int width = (int)((a.tslice_off[slice0 + warp + 1] - o0) >> 5);
+        const int2 *ip = a.tinc + o0 + lane;
+        auto load_entry = [&](int m) { return m < width ? __ldcs(ip + (size_t)m * 32) : make_int2(-1, 0); };
+        int2 e0 = load_entry(0), e1 = load_entry(1);
+        for (int m = 0; m < width; m++) {
+            const int2 e2 = load_entry(m + 2);
+            const int2 cur = e0;
+            e0 = e1; e1 = e2;
+            if (cur.x < 0) continue;                           // slice padding
+            const double2 *src = reinterpret_cast<const double2 *>(Kst + (size_t)cur.x * 4);
+            const double2 k01 = src[0], k23 = src[1];
+            const double kc[4] = {k01.x, k01.y, k23.x, k23.y};
+            const unsigned int sw = (unsigned int)cur.y;
+            // the free dofs of an element are distinct columns of the row, so the NSIZE read-modify-writes of one
+            // incidence are independent: issue every load before the first store (Dirichlet columns share the sink,
+            // whose value is never used)
+            double *dst[NSIZE];
+            double cur_v[NSIZE];
+#pragma unroll
+            for (int j = 0; j < NSIZE; j++) {
+                const unsigned int sl = (sw >> (8 * j)) & 255u;
+                dst[j] = sl == 255u ? dummy : racc + sl;
+            }
+            const double fk = Fst[cur.x];
+#pragma unroll
+            for (int j = 0; j < NSIZE; j++) cur_v[j] = *dst[j];
+#pragma unroll
+            for (int j = 0; j < NSIZE; j++) *dst[j] = cur_v[j] + kc[j];
+            facc = facc + fk;                                  // VecSetValues(ADD)
+        }
+        if (live) a.rhs[tr.x] = facc;
+    }
+    __syncthreads();
+
+    // ---- phase C: accumulators -> CSR values, one warp per row (rows of a tile are runs of consecutive rows) ----
+    for (int i = warp; i < nrows_pad; i += NWARPS) {
+        const int2 tr = __ldg(a.trows + row_off + i);
+        if (tr.x < 0) continue;
+        const int c0 = a.rowptr[tr.x], len = a.rowptr[tr.x + 1] - c0;
+        for (int j = lane; j < len; j += 32) a.val[c0 + j] = acc[tr.y + j];
+    }
+}
+
+}  // namespace pfem

@@ -10,7 +10,18 @@
 // into FMAs, so that Ke/Fe reproduce the gfortran (no-FMA x86-64) results bit for bit.
 // Multiplications by the constant parametric gradients (0, +-1) are exact and are folded away.
 #pragma once
+#ifndef PFEM_EMULATE            // tests/emu compiles this header for the host through a small CUDA shim
 #include <cuda_runtime.h>
+#endif
+
+// keep a value in its register: stops ptxas from rematerialising the product per use (device code only)
+#if defined(__CUDA_ARCH__)
+#define PFEM_KEEP2(a, b) asm volatile("" : "+d"(a), "+d"(b))
+#define PFEM_KEEP3(a, b, c) asm volatile("" : "+d"(a), "+d"(b), "+d"(c))
+#else
+#define PFEM_KEEP2(a, b) ((void)0)
+#define PFEM_KEEP3(a, b, c) ((void)0)
+#endif
 
 namespace pfem {
 
@@ -176,7 +187,7 @@ template <> struct ElemOp<POISSON_TRIA> {
     __device__ __forceinline__ void set_dvol(const Params<POISSON_TRIA> &p) { dvol = p.gw * g.Jac; }               // poisson.F:75
     __device__ __forceinline__ void col_setup(const Params<POISSON_TRIA> &p, int b) {
         px = p.kx * pick(g.dN[0], b); py = p.ky * pick(g.dN[1], b);
-        asm volatile("" : "+d"(px), "+d"(py));     // keep the products: do not rematerialise them per entry
+        PFEM_KEEP2(px, py);                        // keep the products: do not rematerialise them per entry
     }
     __device__ __forceinline__ double K(const Params<POISSON_TRIA> &p, int a) const {                              // :93-95
         const double b1 = pick(g.dN[0], a) * dvol, b2 = pick(g.dN[1], a) * dvol;
@@ -204,7 +215,7 @@ template <> struct ElemOp<POISSON_TETRA> {
     __device__ __forceinline__ void set_dvol(const Params<POISSON_TETRA> &p) { dvol = p.gw * g.Jac; }              // poisson.F:161
     __device__ __forceinline__ void col_setup(const Params<POISSON_TETRA> &p, int b) {
         px = p.kx * pick(g.dN[0], b); py = p.ky * pick(g.dN[1], b); pz = p.kz * pick(g.dN[2], b);
-        asm volatile("" : "+d"(px), "+d"(py), "+d"(pz));
+        PFEM_KEEP3(px, py, pz);
     }
     __device__ __forceinline__ double K(const Params<POISSON_TETRA> &p, int a) const {                             // :183-187
         const double b1 = pick(g.dN[0], a) * dvol, b2 = pick(g.dN[1], a) * dvol, b3 = pick(g.dN[2], a) * dvol;

@@ -145,6 +145,14 @@ struct pfem_solver {
     int asm_rows_per_cta = 0, asm_max_seg = 0;
     size_t asm_smem = 0;
     pfem::DevBuf<int> neg_count;
+    // tiled (compute-once) value pass, opt-in (PFEM_ASM=tiled): tiles.hpp / assembly_tiled.cu
+    bool tiles_ready = false, asm_tiled = false;
+    int last_asm_mode = 0;                 // kernel of the last value pass: 0 generic row gather, 1 streamed row gather, 2 tiled
+    int ntiles = 0, tile_threads = 0;
+    size_t tile_smem = 0;
+    long long tile_elem_visits = 0, tile_elems_touched = 0;
+    pfem::DevBuf<int> t_desc, t_rows, t_el, t_inc;
+    pfem::DevBuf<long long> t_slice_off;
     pfem::DevBuf<char> scratch[8];         // persistent set-up scratch (sort buffers, upload staging), re-used across calls
 
     // solver
@@ -202,6 +210,9 @@ int plan_assembly(pfem_solver *h);
 int assemble_values(pfem_solver *h, const double *elemData, const double *timeData, int *n_neg);
 int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const double *vals, bool transposed,
                 const double *F);
+// assembly_tiled.cu
+int build_tiles_device(pfem_solver *h);
+int assemble_values_tiled(pfem_solver *h, const double *dElemData, const double *dTimeData, bool unit);
 // cg.cu
 int build_solver_structures(pfem_solver *h);
 int cg_solve(pfem_solver *h);

@@ -476,6 +476,8 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof, cons
         PFEM_TRY(build_asm_streams(h));
     }
     h->asm_rows_per_cta = 0;
+    h->tiles_ready = false;            // tiles of the previous pattern (if any) are stale
+    h->asm_tiled = false;
     {
         StageTimer tm("pattern: plan assembly");
         PFEM_TRY(plan_assembly(h));

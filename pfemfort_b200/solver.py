@@ -282,6 +282,12 @@ class SolverB200:
         _chk(self._lib.pfem_solver_comm_mode(self._h, C.byref(m)))
         return m.value
 
+    def assembly_mode(self):
+        """(mode, ntiles, visits_per_element) of the last value pass: 0/1 row gather, 2 tiled compute-once."""
+        m, n, v = C.c_int(), C.c_int(), C.c_double()
+        _chk(self._lib.pfem_solver_assembly_mode(self._h, C.byref(m), C.byref(n), C.byref(v)))
+        return m.value, n.value, v.value
+
     def launch_count(self, reset: bool = False) -> int:
         n = C.c_longlong()
         _chk(self._lib.pfem_solver_launch_count(self._h, C.byref(n), 1 if reset else 0))

@@ -1,0 +1,52 @@
+// cuda_shim.h -- TEST INFRASTRUCTURE ONLY: the handful of CUDA names the tiled value-pass kernel uses, for the host.
+//
+// tests/emu compiles pfemfort_b200/csrc/assembly_tiled.cuh with g++ (-DPFEM_EMULATE -ffp-contract=off) and runs
+// every CTA as a group of OS threads joined by a barrier, so that the kernel's index logic, staging, summation order
+// and arithmetic can be checked against the oracle on a machine without a GPU.  Nothing in the product loads this.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstddef>
+#include <cstdint>
+#include <mutex>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+
+struct int2 { int x, y; };
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(16))) double2 { double x, y; };
+struct uint3 { unsigned int x, y, z; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+extern thread_local uint3 threadIdx, blockIdx;
+extern uint3 blockDim, gridDim;
+
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+static inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+
+// CTA-wide barrier
+struct EmuBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0, waiting = 0;
+    unsigned long long gen = 0;
+    void reset(int n) { count = n; waiting = 0; }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned long long g = gen;
+        if (++waiting == count) { waiting = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+extern EmuBarrier emu_barrier;
+extern unsigned char *emu_smem;
+static inline void __syncthreads() { emu_barrier.wait(); }
+#define PFEM_DYN_SMEM(name) unsigned char *name = emu_smem
