@@ -62,12 +62,13 @@ int build_tiles_device(pfem_solver *h)
     in.rec_ints = h->rec_ints; in.ndim = h->ndim; in.xyz_stride = stride;
     in.erec = erec.data(); in.xyz = xyz.data(); in.rowptr = rowptr.data(); in.rinc_ptr = rinc_ptr.data();
     in.rinc = rinc.data(); in.ainc_off = ainc_off.data(); in.ainc = ainc.data(); in.ainc_words = h->ainc_words;
-    // tuning hooks: CTA size (128 | 256), rows per tile, shared memory per CTA.  Defaults: 128 threads, 96 rows,
-    // 110 KB => two CTAs per SM, so that one CTA's gather phase overlaps the other's FP64 phase.
-    in.cta_threads = env_int("PFEM_TILE_THREADS", 128) == 256 ? 256 : 128;
-    in.max_rows = env_int("PFEM_TILE_ROWS", in.cta_threads == 256 ? 192 : 96);
+    // tuning hooks: CTA size (128 | 256 | 512), rows per tile, shared memory per CTA.  Defaults: 256 threads, 96 rows,
+    // 110 KB => two CTAs (16 warps) per SM, so that one CTA's gather phase overlaps the other's FP64 phase.
+    in.cta_threads = env_int("PFEM_TILE_THREADS", 256);
+    if (in.cta_threads != 128 && in.cta_threads != 512) in.cta_threads = 256;
+    in.max_rows = env_int("PFEM_TILE_ROWS", in.cta_threads == 512 ? 192 : 96);
     in.max_rows = std::max(32, std::min(in.cta_threads, in.max_rows / 32 * 32));
-    const int kb = env_int("PFEM_TILE_SMEM_KB", in.cta_threads == 256 ? 220 : 110);
+    const int kb = env_int("PFEM_TILE_SMEM_KB", in.cta_threads == 512 ? 220 : 110);
     in.smem_budget = std::min((size_t)kb * 1024, (size_t)max_smem_optin);
     TileSet ts;
     if (build_tiles(in, ts) != 0) return PFEM_OK;              // declined: keep the row-gather kernel
@@ -124,10 +125,13 @@ int assemble_values_tiled(pfem_solver *h, const double *dElemData, const double 
     a.neg_flag = h->neg_count.p;
     a.load_val = h->values_zero ? 0 : 1; a.load_rhs = h->rhs_zero ? 0 : 1;
     if (h->ntiles == 0) return PFEM_OK;
+    // CTA shapes: 128 threads x 4 CTAs/SM (small tiles), 256 x 2 (default), 512 x 1 (large tiles): 16 warps per SM each
     if (h->kind == PFEM_POISSON_TETRA)
-        return h->tile_threads == 256 ? launch_tiled<POISSON_TETRA, 256, 1>(h, a, unit) : launch_tiled<POISSON_TETRA, 128, 2>(h, a, unit);
+        return h->tile_threads == 512 ? launch_tiled<POISSON_TETRA, 512, 1>(h, a, unit)
+             : h->tile_threads == 256 ? launch_tiled<POISSON_TETRA, 256, 2>(h, a, unit) : launch_tiled<POISSON_TETRA, 128, 4>(h, a, unit);
     if (h->kind == PFEM_POISSON_TRIA)
-        return h->tile_threads == 256 ? launch_tiled<POISSON_TRIA, 256, 1>(h, a, unit) : launch_tiled<POISSON_TRIA, 128, 2>(h, a, unit);
+        return h->tile_threads == 512 ? launch_tiled<POISSON_TRIA, 512, 1>(h, a, unit)
+             : h->tile_threads == 256 ? launch_tiled<POISSON_TRIA, 256, 2>(h, a, unit) : launch_tiled<POISSON_TRIA, 128, 4>(h, a, unit);
     set_error("tiled value pass: kind %d is not a one-dof-per-node kind", h->kind);
     return PFEM_ERR_STATE;
 }

@@ -54,6 +54,17 @@ __device__ __forceinline__ void tiled_ld_xyz(const double *p, double &x, double 
 __device__ __forceinline__ double tiled_kcoef(const Params<POISSON_TRIA> &p, int d) { return d == 0 ? p.kx : p.ky; }
 __device__ __forceinline__ double tiled_kcoef(const Params<POISSON_TETRA> &p, int d) { return d == 0 ? p.kx : (d == 1 ? p.ky : p.kz); }
 
+// Staging layout in shared memory.  A staged column is 4 doubles = two 16-byte chunks; four columns share a 128-byte
+// line.  In phase A consecutive lanes write columns 4 apart (one element each), i.e. the same chunk of consecutive lines:
+// the chunk index is XOR-swizzled with the line number so that the 8 lanes of a quarter warp hit 8 different bank
+// groups.  Flocal is stored structure-of-arrays by (column & 3) for the same reason.
+__device__ __forceinline__ int tiled_kst_off(int col, int half)      // in doubles
+{
+    const int line = col >> 2, chunk = ((((col & 3) << 1) | half) ^ line) & 7;
+    return line * 16 + chunk * 2;
+}
+__device__ __forceinline__ int tiled_fst_off(int col, int nlines) { return (col & 3) * nlines + (col >> 2); }
+
 #ifndef PFEM_DYN_SMEM
 #define PFEM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -71,9 +82,10 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const Til
     const int *td = a.tdesc + (size_t)blockIdx.x * TILE_DESC_INTS;
     const int row_off = td[TD_ROW_OFF], nrows_pad = td[TD_NROWS_PAD], el_off = td[TD_EL_OFF], nel = td[TD_NEL];
     const int slice0 = td[TD_SLICE0], nnz = td[TD_NNZ], ncols = td[TD_NCOLS];
-    double *Kst = reinterpret_cast<double *>(smem_raw);      // [ncols][4]: Klocal(0..NSIZE-1, k) of a staged column
-    double *Fst = Kst + (size_t)ncols * 4;                   // [ncols]   : lifted Flocal(k)
-    double *acc = Fst + ncols;                               // [nnz]     : the tile's CSR values, tile-row order
+    const int nlines = (ncols + 3) >> 2;
+    double *Kst = reinterpret_cast<double *>(smem_raw);      // [nlines][16]: Klocal(0..NSIZE-1, k) of the staged columns (swizzled)
+    double *Fst = Kst + (size_t)nlines * 16;                 // [4][nlines] : lifted Flocal(k)
+    double *acc = Fst + (size_t)nlines * 4;                  // [nnz]       : the tile's CSR values, tile-row order
     double *sink = acc + nnz;                                // [THREADS] : Dirichlet columns land here (never used)
 
     // ---- accumulators: zero, or the current values when the matrix was not zeroed since the last pass ----
@@ -178,10 +190,9 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const Til
                     }
                 }
                 if (neg) { kc[0] = kc[1] = kc[2] = kc[3] = 0.0; f = 0.0; }
-                double2 *dst = reinterpret_cast<double2 *>(Kst + (size_t)col * 4);
-                dst[0] = make_double2(kc[0], kc[1]);
-                dst[1] = make_double2(kc[2], kc[3]);
-                Fst[col] = f;
+                *reinterpret_cast<double2 *>(Kst + tiled_kst_off(col, 0)) = make_double2(kc[0], kc[1]);
+                *reinterpret_cast<double2 *>(Kst + tiled_kst_off(col, 1)) = make_double2(kc[2], kc[3]);
+                Fst[tiled_fst_off(col, nlines)] = f;
                 col++;
             }
         }
@@ -205,8 +216,8 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const Til
             const int2 cur = e0;
             e0 = e1; e1 = e2;
             if (cur.x < 0) continue;                           // slice padding
-            const double2 *src = reinterpret_cast<const double2 *>(Kst + (size_t)cur.x * 4);
-            const double2 k01 = src[0], k23 = src[1];
+            const double2 k01 = *reinterpret_cast<const double2 *>(Kst + tiled_kst_off(cur.x, 0));
+            const double2 k23 = *reinterpret_cast<const double2 *>(Kst + tiled_kst_off(cur.x, 1));
             const double kc[4] = {k01.x, k01.y, k23.x, k23.y};
             const unsigned int sw = (unsigned int)cur.y;
             // the free dofs of an element are distinct columns of the row, so the NSIZE read-modify-writes of one
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const Til
                 const unsigned int sl = (sw >> (8 * j)) & 255u;
                 dst[j] = sl == 255u ? dummy : racc + sl;
             }
-            const double fk = Fst[cur.x];
+            const double fk = Fst[tiled_fst_off(cur.x, nlines)];
 #pragma unroll
             for (int j = 0; j < NSIZE; j++) cur_v[j] = *dst[j];
 #pragma unroll

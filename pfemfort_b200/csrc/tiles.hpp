@@ -52,7 +52,8 @@ struct TileSet {
 // bytes of dynamic shared memory a tile needs: staged columns (4 doubles of Klocal + 1 of Flocal), accumulators, sinks
 inline size_t tile_smem_bytes(long long ncols, long long nnz, int cta_threads)
 {
-    return (size_t)ncols * 40 + (size_t)nnz * 8 + (size_t)cta_threads * 8 + 32;
+    const size_t nlines = (size_t)(ncols + 3) / 4;              // four staged columns per 128-byte line (+ 4 Flocal)
+    return nlines * 160 + (size_t)nnz * 8 + (size_t)cta_threads * 8 + 32;
 }
 
 inline uint64_t morton_spread3(uint64_t v)

@@ -145,6 +145,7 @@ extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *con
     } while (0)
     if (threads == 128) { if (kind == POISSON_TRIA) RUN(POISSON_TRIA, 128); else RUN(POISSON_TETRA, 128); }
     else if (threads == 256) { if (kind == POISSON_TRIA) RUN(POISSON_TRIA, 256); else RUN(POISSON_TETRA, 256); }
+    else if (threads == 512) { if (kind == POISSON_TRIA) RUN(POISSON_TRIA, 512); else RUN(POISSON_TETRA, 512); }
     else return 3;
     if (stats) {
         stats[0] = ts.ntiles; stats[1] = ts.elem_visits; stats[2] = ts.elems_touched; stats[3] = (long long)ts.max_smem;

@@ -53,7 +53,7 @@ CASES = {
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("threads,rows", [(128, 96), (128, 32), (256, 192)])
+@pytest.mark.parametrize("threads,rows", [(256, 96), (128, 32), (512, 192)])
 def test_tiled_value_pass_bit_identical(gpu, input_dir, tiled_env, name, threads, rows):
     m, kind = CASES[name](input_dir)
     num = D.number(m, kind)

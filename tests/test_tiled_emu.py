@@ -80,7 +80,7 @@ def _check(res):
 
 
 @pytest.mark.parametrize("name,kind", [("tria20x20", S.POISSON_TRIA), ("tet10", S.POISSON_TETRA)])
-@pytest.mark.parametrize("tile_rows,threads", [(32, 128), (96, 128), (128, 128), (256, 256)])
+@pytest.mark.parametrize("tile_rows,threads", [(32, 128), (96, 128), (128, 128), (96, 256), (256, 256), (192, 512)])
 def test_fixtures_bit_exact(emu, input_dir, name, kind, tile_rows, threads):
     m = M.read_mesh(os.path.join(input_dir, name))
     num = D.number(m, kind)
