@@ -113,7 +113,7 @@ int assemble_values_tiled(pfem_solver *h, const double *dElemData, const double 
 {
     TiledArgs a;
     a.tdesc = h->t_desc.p;
-    a.trows = reinterpret_cast<const int2 *>(h->t_rows.p);
+    a.trows = reinterpret_cast<const int4 *>(h->t_rows.p);
     a.tel = reinterpret_cast<const int2 *>(h->t_el.p);
     a.tslice_off = h->t_slice_off.p;
     a.tinc = reinterpret_cast<const int2 *>(h->t_inc.p);

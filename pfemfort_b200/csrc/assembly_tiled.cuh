@@ -25,7 +25,7 @@ namespace pfem {
 
 struct TiledArgs {
     const int *tdesc;                 // [ntiles][TILE_DESC_INTS]
-    const int2 *trows;                // { local row or -1, accumulator offset }
+    const int4 *trows;                // { local row or -1, accumulator offset, rowptr[row], row length }
     const int2 *tel;                  // { e | dbc<<31, base | mask<<24 }
     const long long *tslice_off;
     const int2 *tinc;                 // { staged column or -1, slot bytes }
@@ -94,11 +94,19 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const Til
         for (int q = tid; q < nnz; q += THREADS) acc[q] = 0.0;
     } else {
         for (int i = warp; i < nrows_pad; i += NWARPS) {
-            const int2 tr = __ldg(a.trows + row_off + i);
+            const int4 tr = __ldg(a.trows + row_off + i);
             if (tr.x < 0) continue;
-            const int c0 = a.rowptr[tr.x], len = a.rowptr[tr.x + 1] - c0;
-            for (int j = lane; j < len; j += 32) acc[tr.y + j] = a.val[c0 + j];
+            for (int j = lane; j < tr.w; j += 32) acc[tr.y + j] = a.val[tr.z + j];
         }
+    }
+    // the row threads' own stream heads: issued now, consumed in phase B (in flight during phase A)
+    int4 my_tr = make_int4(-1, 0, 0, 0);
+    long long my_o0 = 0;
+    int my_width = 0;
+    if (tid < nrows_pad) {
+        my_tr = __ldg(a.trows + row_off + tid);
+        my_o0 = a.tslice_off[slice0 + warp];
+        my_width = (int)((a.tslice_off[slice0 + warp + 1] - my_o0) >> 5);
     }
 
     // ---- phase A: every element of the tile once ----
@@ -197,56 +205,67 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const Til
             }
         }
     }
-    __syncthreads();
-
     // ---- phase B: one thread per tile row gathers its staged columns in ascending element id ----
+    // The incidence entries are streamed in batches of NB per row, the next batch in flight while the current one is
+    // consumed (an entry costs ~60 cycles of shared-memory work, far less than one HBM latency); the first batch is
+    // issued before the barrier.
+    constexpr int NB = 8;
+    const int2 *ip = a.tinc + my_o0 + lane;
+    auto load_entry = [&](int m) { return m < my_width ? __ldcs(ip + (size_t)m * 32) : make_int2(-1, 0); };
+    int2 buf[NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) buf[q] = load_entry(q);
+    __syncthreads();
     if (tid < nrows_pad) {
-        const int2 tr = __ldg(a.trows + row_off + tid);
+        const int4 tr = my_tr;
         const bool live = tr.x >= 0;
         double *racc = acc + tr.y;
         double *dummy = sink + tid;
         double facc = (live && a.load_rhs) ? a.rhs[tr.x] : 0.0;
-        const long long o0 = a.tslice_off[slice0 + warp];
-        const int width = (int)((a.tslice_off[slice0 + warp + 1] - o0) >> 5);
-        const int2 *ip = a.tinc + o0 + lane;
-        auto load_entry = [&](int m) { return m < width ? __ldcs(ip + (size_t)m * 32) : make_int2(-1, 0); };
-        int2 e0 = load_entry(0), e1 = load_entry(1);
-        for (int m = 0; m < width; m++) {
-            const int2 e2 = load_entry(m + 2);
-            const int2 cur = e0;
-            e0 = e1; e1 = e2;
-            if (cur.x < 0) continue;                           // slice padding
-            const double2 k01 = *reinterpret_cast<const double2 *>(Kst + tiled_kst_off(cur.x, 0));
-            const double2 k23 = *reinterpret_cast<const double2 *>(Kst + tiled_kst_off(cur.x, 1));
-            const double kc[4] = {k01.x, k01.y, k23.x, k23.y};
-            const unsigned int sw = (unsigned int)cur.y;
-            // the free dofs of an element are distinct columns of the row, so the NSIZE read-modify-writes of one
-            // incidence are independent: issue every load before the first store (Dirichlet columns share the sink,
-            // whose value is never used)
-            double *dst[NSIZE];
-            double cur_v[NSIZE];
+        for (int m0 = 0; m0 < my_width; m0 += NB) {
+            int2 nxt[NB];
 #pragma unroll
-            for (int j = 0; j < NSIZE; j++) {
-                const unsigned int sl = (sw >> (8 * j)) & 255u;
-                dst[j] = sl == 255u ? dummy : racc + sl;
+            for (int q = 0; q < NB; q++) nxt[q] = load_entry(m0 + NB + q);
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                const int2 cur = buf[q];
+                if (cur.x >= 0) {                              // (< 0: slice padding)
+                    const double2 k01 = *reinterpret_cast<const double2 *>(Kst + tiled_kst_off(cur.x, 0));
+                    const double2 k23 = *reinterpret_cast<const double2 *>(Kst + tiled_kst_off(cur.x, 1));
+                    const double kc[4] = {k01.x, k01.y, k23.x, k23.y};
+                    const unsigned int sw = (unsigned int)cur.y;
+                    // the free dofs of an element are distinct columns of the row, so the NSIZE read-modify-writes of
+                    // one incidence are independent: issue every load before the first store (Dirichlet columns share
+                    // the sink, whose value is never used)
+                    double *dst[NSIZE];
+                    double cur_v[NSIZE];
+#pragma unroll
+                    for (int j = 0; j < NSIZE; j++) {
+                        const unsigned int sl = (sw >> (8 * j)) & 255u;
+                        dst[j] = sl == 255u ? dummy : racc + sl;
+                    }
+                    const double fk = Fst[tiled_fst_off(cur.x, nlines)];
+#pragma unroll
+                    for (int j = 0; j < NSIZE; j++) cur_v[j] = *dst[j];
+#pragma unroll
+                    for (int j = 0; j < NSIZE; j++) *dst[j] = cur_v[j] + kc[j];
+                    facc = facc + fk;                          // VecSetValues(ADD)
+                }
             }
-            const double fk = Fst[tiled_fst_off(cur.x, nlines)];
 #pragma unroll
-            for (int j = 0; j < NSIZE; j++) cur_v[j] = *dst[j];
-#pragma unroll
-            for (int j = 0; j < NSIZE; j++) *dst[j] = cur_v[j] + kc[j];
-            facc = facc + fk;                                  // VecSetValues(ADD)
+            for (int q = 0; q < NB; q++) buf[q] = nxt[q];
         }
         if (live) a.rhs[tr.x] = facc;
     }
     __syncthreads();
 
     // ---- phase C: accumulators -> CSR values, one warp per row (rows of a tile are runs of consecutive rows) ----
+    // (the row descriptors carry rowptr[row] and the row length: no dependent global load per row)
+#pragma unroll 4
     for (int i = warp; i < nrows_pad; i += NWARPS) {
-        const int2 tr = __ldg(a.trows + row_off + i);
+        const int4 tr = __ldg(a.trows + row_off + i);
         if (tr.x < 0) continue;
-        const int c0 = a.rowptr[tr.x], len = a.rowptr[tr.x + 1] - c0;
-        for (int j = lane; j < len; j += 32) a.val[c0 + j] = acc[tr.y + j];
+        for (int j = lane; j < tr.w; j += 32) a.val[tr.z + j] = acc[tr.y + j];
     }
 }
 

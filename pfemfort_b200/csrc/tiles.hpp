@@ -40,7 +40,7 @@ struct TileSet {
     int ntiles = 0;
     long long nslices = 0;
     std::vector<int> tdesc;               // [ntiles][TILE_DESC_INTS]
-    std::vector<int> trows;               // int2 per padded tile row: { local row or -1, accumulator offset }
+    std::vector<int> trows;               // int4 per padded tile row: { local row or -1, accumulator offset, rowptr[row], row length }
     std::vector<int> tel;                 // int2 per tile element: { e | dbc<<31, base | mask<<24 }
     std::vector<long long> tslice_off;    // [nslices+1] entry offsets into tinc
     std::vector<int> tinc;                // int2 per entry: { staged column or -1, slot bytes }
@@ -175,7 +175,7 @@ inline int build_tiles(const TileInput &in, TileSet &out)
     out.tslice_off.assign((size_t)out.nslices + 1, 0);
     for (long long s = 0; s < out.nslices; s++) out.tslice_off[s + 1] = out.tslice_off[s] + slice_sz[s];
     if (out.tslice_off[out.nslices] >= (1LL << 30)) return 1;
-    out.trows.assign((size_t)row_off[ntiles] * 2, -1);
+    out.trows.assign((size_t)row_off[ntiles] * 4, 0);
     out.tel.assign((size_t)el_off[ntiles] * 2, 0);
     out.tinc.assign((size_t)out.tslice_off[out.nslices] * 2, -1);
     out.elem_visits = el_off[ntiles];
@@ -219,12 +219,14 @@ inline int build_tiles(const TileInput &in, TileSet &out)
             te[2 * i + 1] = base[i] | ((int)mask[i] << 24);
         }
         // rows, accumulator offsets, incidence entries (SELL-32 inside the tile: slice = 32 tile rows, column-major)
-        int *tr = out.trows.data() + (size_t)row_off[t] * 2;
+        int *tr = out.trows.data() + (size_t)row_off[t] * 4;
         int acc = 0;
         for (int i = 0; i < n; i++) {
             const int r = order[q0 + i].second;
-            tr[2 * i] = r;
-            tr[2 * i + 1] = acc;
+            tr[4 * i] = r;
+            tr[4 * i + 1] = acc;
+            tr[4 * i + 2] = in.rowptr[r];
+            tr[4 * i + 3] = in.rowptr[r + 1] - in.rowptr[r];
             acc += in.rowptr[r + 1] - in.rowptr[r];
             const long long so = out.tslice_off[slice_cnt[t] + i / 32] + (i & 31);
             const long long ao = in.ainc_off[r >> 5] + (r & 31);
@@ -240,7 +242,7 @@ inline int build_tiles(const TileInput &in, TileSet &out)
                 dst[1] = src[1];
             }
         }
-        for (int i = n; i < tile_pad[t]; i++) tr[2 * i + 1] = acc;
+        for (int i = n; i < tile_pad[t]; i++) { tr[4 * i] = -1; tr[4 * i + 1] = acc; }
         int *td = out.tdesc.data() + (size_t)t * TILE_DESC_INTS;
         td[TD_ROW_OFF] = (int)row_off[t]; td[TD_NROWS_PAD] = tile_pad[t]; td[TD_EL_OFF] = (int)el_off[t]; td[TD_NEL] = nel;
         td[TD_SLICE0] = (int)slice_cnt[t]; td[TD_NNZ] = acc; td[TD_NCOLS] = base[nel]; td[TD_NROWS] = n;

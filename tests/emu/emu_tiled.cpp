@@ -126,7 +126,9 @@ extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *con
     int neg_flag = 0;
     TiledArgs a;
     a.tdesc = ts.tdesc.data();
-    a.trows = reinterpret_cast<const int2 *>(ts.trows.data());
+    std::vector<int4> trows4(ts.trows.size() / 4 + 1);
+    std::memcpy(trows4.data(), ts.trows.data(), ts.trows.size() * sizeof(int));
+    a.trows = trows4.data();
     a.tel = reinterpret_cast<const int2 *>(ts.tel.data());
     a.tslice_off = ts.tslice_off.data();
     a.tinc = reinterpret_cast<const int2 *>(ts.tinc.data());

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pfemfort_b200 import driver as D, mesh as M, solver as S  # noqa: E402
 
-VARIANTS = [(256, 96, 110), (512, 192, 220), (128, 32, 40)]      # threads, rows per tile, KB of shared memory per CTA
+VARIANTS = [(256, 96, 110), (128, 64, 72), (512, 192, 220)]      # threads, rows per tile, KB of shared memory per CTA
 
 
 def one_pass(m, kind, num, reps=3):
