@@ -326,6 +326,28 @@ def main():
     asm_gbs = asm_b * args.steps / (t_asm if t_asm > 0 else 1) / 1e9
     cgit_gbs = cgit_b * its / t_solve / 1e9
 
+    # FP64 pipe of the value pass (BASELINE.json north_star: "with the FP64 pipe reported for the element kernels"):
+    # the row-gather kernel issues 114 FP64 instructions per (row, element) incidence (no FMA by design: bit-identical to
+    # the reference's evaluation order), 4 incidences per tetrahedron; peak = SMs x 64 FP64 lanes x the SM clock under load.
+    asm_fp64 = None
+    asm_kernel = None
+    try:
+        asm_mode = s.assembly_mode()
+        asm_kernel = {0: "assemble_kernel (row gather, binary-search slots)", 1: "assemble_sell_kernel (streamed row gather)",
+                      2: f"assemble_tiled_kernel (compute-once tiles: {asm_mode[1]} tiles, {asm_mode[2]:.2f} visits/element)"}[asm_mode[0]]
+        if asm_mode[0] != 1:
+            raise RuntimeError("FP64 instruction count below is the row-gather kernel's")
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+        fp64_ops = 114.0 * 4.0 * conn.shape[1]
+        fp64_peak = sm_count * 64 * mhz * 1e6
+        fp64_rate = fp64_ops * args.steps / (t_asm if t_asm > 0 else 1)
+        asm_fp64 = {"ops_per_launch": fp64_ops, "achieved_gops": fp64_rate / 1e9, "peak_gops": fp64_peak / 1e9,
+                    "frac": fp64_rate / fp64_peak, "unit": "FP64 instr/s (DADD/DMUL, no FMA by design)",
+                    "peak_source": f"{sm_count} SMs x 64 lanes x {mhz:.0f} MHz (SM clock sampled under load)"}
+    except Exception:        # reporting only: never fail the bench on it
+        asm_fp64 = None
+
     # ---- end-to-end leg: host buffers in, solution out, every step ----
     e2e_t = 0.0
     e2e_its = 0
@@ -367,7 +389,8 @@ def main():
                      "ms_per_pass": 1e3 * t_asm / args.steps,
                      "roofline": {"bound": "hbm (kernel is FP64-pipe/issue bound, see DESIGN.md)", "achieved": asm_gbs, "peak": peak,
                                   "unit": "GB/s", "frac": asm_gbs / peak,
-                                  "traffic": (3.552e9 if (world == 1 and args.cells == 200) else None), "bytes_per_launch": asm_b, "peak_source": peak_src, "scope": "rank 0 share"}},
+                                  "traffic": (3.552e9 if (world == 1 and args.cells == 200) else None), "bytes_per_launch": asm_b, "peak_source": peak_src, "scope": "rank 0 share"},
+                     "kernel": asm_kernel, "fp64_pipe": asm_fp64},
         "cg_iteration": {"ms_per_iteration": 1e3 * t_solve / max(its, 1), "achieved_gbs": cgit_gbs, "frac": cgit_gbs / peak,
                          "bytes_per_iteration": cgit_b},
         # dominant kernel = the persistent CG kernel (one cooperative launch per solve: set-up + every iteration);
