@@ -438,8 +438,9 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     a.unit = (td[1] == 1.0 && ed[0] == 1.0 && ed[1] == 1.0 && (h->kind == PFEM_POISSON_TRIA || ed[2] == 1.0)) ? 1 : 0;
     // opt-in: the tiled (compute-once) kernel for the one-dof-per-node kinds; tiles are built once per pattern
     const char *mode = getenv("PFEM_ASM");
-    const bool want_tiled = mode && !strcmp(mode, "tiled") && h->ndof == 1;
-    if (want_tiled && !h->tiles_ready) PFEM_TRY(build_tiles_device(h));
+    const int tile_mode = !mode ? 0 : !strcmp(mode, "tiled") ? 1 : !strcmp(mode, "tiled2") ? 2 : 0;
+    const bool want_tiled = tile_mode != 0 && h->ndof == 1;
+    if (want_tiled && (!h->tiles_ready || h->tile_mode != tile_mode)) PFEM_TRY(build_tiles_device(h, tile_mode));
     PFEM_CUDA(cudaEventRecord(h->ev0, s));
     int st = PFEM_OK;
     h->last_asm_mode = (want_tiled && h->asm_tiled) ? 2 : (h->asm_sell ? 1 : 0);

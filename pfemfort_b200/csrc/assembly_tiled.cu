@@ -1,5 +1,6 @@
-// assembly_tiled.cu -- set-up and launch of the tiled (compute-once) value pass (kernel: assembly_tiled.cuh,
-// tile construction: tiles.hpp).  Opt-in with PFEM_ASM=tiled for the one-dof-per-node kinds (Poisson tria/tet);
+// assembly_tiled.cu -- set-up and launch of the tiled (compute-once) value pass (kernels: assembly_tiled.cuh,
+// tile construction: tiles.hpp).  Opt-in with PFEM_ASM=tiled (staged columns + row gather) or PFEM_ASM=tiled2
+// (sorted scatter + run sums) for the one-dof-per-node kinds (Poisson tria/tet);
 // everything else, and any mesh the tile builder declines, stays on the row-gather kernels of assembly.cu.
 //
 // Compiled with -fmad=false like assembly.cu: the element arithmetic must not be contracted into FMAs.
@@ -33,10 +34,11 @@ static int env_int(const char *name, int dflt)
 // Build the tiles of the current pattern (once per pattern pass).  The first version runs the construction on the
 // host from copies of the pattern-pass arrays: it is set-up work (the reference's own pattern pass is host code).
 // On return h->asm_tiled tells whether the tiled kernel can be used.
-int build_tiles_device(pfem_solver *h)
+int build_tiles_device(pfem_solver *h, int mode)
 {
     h->tiles_ready = true;
     h->asm_tiled = false;
+    h->tile_mode = mode;
     if (h->ndof != 1 || !h->asm_sell || h->size_local == 0) return PFEM_OK;
     StageTimer tm("assembly: build tiles (host)");
     cudaStream_t s = h->stream;
@@ -68,7 +70,8 @@ int build_tiles_device(pfem_solver *h)
     if (in.cta_threads != 128 && in.cta_threads != 512) in.cta_threads = 256;
     in.max_rows = env_int("PFEM_TILE_ROWS", in.cta_threads == 512 ? 192 : 96);
     in.max_rows = std::max(32, std::min(in.cta_threads, in.max_rows / 32 * 32));
-    const int kb = env_int("PFEM_TILE_SMEM_KB", in.cta_threads == 512 ? 220 : 110);
+    const int kb = env_int("PFEM_TILE_SMEM_KB", in.cta_threads == 512 ? 220 : (mode == 2 ? 112 : 110));
+    in.mode = mode;
     in.smem_budget = std::min((size_t)kb * 1024, (size_t)max_smem_optin);
     TileSet ts;
     if (build_tiles(in, ts) != 0) return PFEM_OK;              // declined: keep the row-gather kernel
@@ -77,6 +80,9 @@ int build_tiles_device(pfem_solver *h)
     PFEM_TRY(push(h->t_el, ts.tel, s));
     PFEM_TRY(push(h->t_slice_off, ts.tslice_off, s));
     PFEM_TRY(push(h->t_inc, ts.tinc, s));
+    PFEM_TRY(push(h->t_crec, ts.crec, s));
+    PFEM_TRY(push(h->t_cnt, ts.cnt, s));
+    PFEM_TRY(push(h->t_ts2, ts.ts2, s));
     PFEM_CUDA(cudaStreamSynchronize(s));
     h->ntiles = ts.ntiles;
     h->tile_threads = in.cta_threads;
@@ -95,7 +101,15 @@ template <int KIND, int THREADS, int MINB>
 static int launch_tiled(pfem_solver *h, const TiledArgs &a, bool unit)
 {
     const size_t smem = h->tile_smem;
-    if (unit) {
+    if (h->tile_mode == 2) {
+        if (unit) {
+            PFEM_CUDA(cudaFuncSetAttribute(assemble_tiled2_kernel<KIND, THREADS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            assemble_tiled2_kernel<KIND, THREADS, MINB, true><<<h->ntiles, THREADS, smem, h->stream>>>(a);
+        } else {
+            PFEM_CUDA(cudaFuncSetAttribute(assemble_tiled2_kernel<KIND, THREADS, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            assemble_tiled2_kernel<KIND, THREADS, MINB, false><<<h->ntiles, THREADS, smem, h->stream>>>(a);
+        }
+    } else if (unit) {
         PFEM_CUDA(cudaFuncSetAttribute(assemble_tiled_kernel<KIND, THREADS, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         assemble_tiled_kernel<KIND, THREADS, MINB, true><<<h->ntiles, THREADS, smem, h->stream>>>(a);
     } else {
@@ -117,6 +131,9 @@ int assemble_values_tiled(pfem_solver *h, const double *dElemData, const double 
     a.tel = reinterpret_cast<const int2 *>(h->t_el.p);
     a.tslice_off = h->t_slice_off.p;
     a.tinc = reinterpret_cast<const int2 *>(h->t_inc.p);
+    a.crec = reinterpret_cast<const int2 *>(h->t_crec.p);
+    a.cnt = reinterpret_cast<const uint4 *>(h->t_cnt.p);
+    a.ts2 = reinterpret_cast<const int4 *>(h->t_ts2.p);
     a.conn4 = reinterpret_cast<const int4 *>(h->conn4.p);
     a.erec = h->erec.p; a.rec_ints = h->rec_ints;
     a.xyz = h->xyz.p; a.applied = h->applied.p; a.rowptr = h->rowptr.p;

@@ -151,7 +151,9 @@ struct pfem_solver {
     int ntiles = 0, tile_threads = 0;
     size_t tile_smem = 0;
     long long tile_elem_visits = 0, tile_elems_touched = 0;
-    pfem::DevBuf<int> t_desc, t_rows, t_el, t_inc;
+    int tile_mode = 0;                     // 1: gather kernel (PFEM_ASM=tiled), 2: scatter kernel (PFEM_ASM=tiled2)
+    pfem::DevBuf<int> t_desc, t_rows, t_el, t_inc, t_crec, t_ts2;
+    pfem::DevBuf<unsigned char> t_cnt;
     pfem::DevBuf<long long> t_slice_off;
     pfem::DevBuf<char> scratch[8];         // persistent set-up scratch (sort buffers, upload staging), re-used across calls
 
@@ -211,7 +213,7 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
 int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const double *vals, bool transposed,
                 const double *F);
 // assembly_tiled.cu
-int build_tiles_device(pfem_solver *h);
+int build_tiles_device(pfem_solver *h, int mode);
 int assemble_values_tiled(pfem_solver *h, const double *dElemData, const double *dTimeData, bool unit);
 // cg.cu
 int build_solver_structures(pfem_solver *h);

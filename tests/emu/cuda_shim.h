@@ -20,10 +20,14 @@
 struct int2 { int x, y; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 struct __attribute__((aligned(16))) double2 { double x, y; };
+struct __attribute__((aligned(16))) uint4 { unsigned int x, y, z, w; };
+static inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
 struct uint3 { unsigned int x, y, z; };
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+static inline int min(int a, int b) { return a < b ? a : b; }
 
 extern thread_local uint3 threadIdx, blockIdx;
 extern uint3 blockDim, gridDim;

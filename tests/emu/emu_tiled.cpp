@@ -22,7 +22,7 @@ unsigned char *emu_smem = nullptr;
 using namespace pfem;
 
 template <int KIND, int THREADS, bool UNIT>
-static void run_grid(const TiledArgs &args, int ntiles, size_t smem_bytes)
+static void run_grid(const TiledArgs &args, int ntiles, size_t smem_bytes, int mode)
 {
     std::vector<unsigned char> smem(smem_bytes + 64);
     unsigned char *base = smem.data();
@@ -38,7 +38,8 @@ static void run_grid(const TiledArgs &args, int ntiles, size_t smem_bytes)
             threadIdx = uint3{(unsigned)t, 0, 0};
             for (int b = 0; b < ntiles; b++) {
                 blockIdx = uint3{(unsigned)b, 0, 0};
-                assemble_tiled_kernel<KIND, THREADS, 1, UNIT>(args);
+                if (mode == 2) assemble_tiled2_kernel<KIND, THREADS, 1, UNIT>(args);
+                else assemble_tiled_kernel<KIND, THREADS, 1, UNIT>(args);
                 emu_barrier.wait();
                 if (t == 0) std::memset(base, 0xFF, smem_bytes);
                 emu_barrier.wait();
@@ -53,7 +54,7 @@ static void run_grid(const TiledArgs &args, int ntiles, size_t smem_bytes)
 extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *conn0, const int *edof, const double *xyz_soa,
                                   const double *applied, int row_lo, int nloc, const int *rowptr, const int *col,
                                   const double *elemData, const double *timeData, int tile_rows, int smem_budget, int threads,
-                                  int load, double *val, double *rhs, long long *stats)
+                                  int load, double *val, double *rhs, long long *stats, int mode)
 {
     if (kind != POISSON_TRIA && kind != POISSON_TETRA) return 2;
     const bool build_only = threads < 0;          // tile statistics only (large meshes: the emulated kernel is slow)
@@ -114,6 +115,7 @@ extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *con
     in.ndim = ndim; in.xyz_stride = stride; in.erec = erec.data(); in.xyz = xyz.data(); in.rowptr = rowptr;
     in.rinc_ptr = rinc_ptr.data(); in.rinc = rinc.data(); in.ainc_off = ainc_off.data(); in.ainc = ainc.data();
     in.ainc_words = 2; in.max_rows = tile_rows; in.smem_budget = (size_t)smem_budget; in.cta_threads = threads;
+    in.mode = mode == 2 ? 2 : 1;
     TileSet ts;
     if (build_tiles(in, ts) != 0) return 1;
     if (stats) { stats[0] = ts.ntiles; stats[1] = ts.elem_visits; stats[2] = ts.elems_touched; stats[3] = (long long)ts.max_smem; stats[4] = 0; }
@@ -132,6 +134,13 @@ extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *con
     a.tel = reinterpret_cast<const int2 *>(ts.tel.data());
     a.tslice_off = ts.tslice_off.data();
     a.tinc = reinterpret_cast<const int2 *>(ts.tinc.data());
+    std::vector<uint4> cnt4(ts.cnt.size() / 16 + 1);
+    if (!ts.cnt.empty()) std::memcpy(cnt4.data(), ts.cnt.data(), ts.cnt.size());
+    a.crec = reinterpret_cast<const int2 *>(ts.crec.data());
+    a.cnt = cnt4.data();
+    std::vector<int4> ts24(ts.ts2.size() / 4 + 1);
+    if (!ts.ts2.empty()) std::memcpy(ts24.data(), ts.ts2.data(), ts.ts2.size() * sizeof(int));
+    a.ts2 = ts24.data();
     std::vector<int4> c4(nElem);
     std::memcpy(c4.data(), conn4.data(), (size_t)nElem * sizeof(int4));
     a.conn4 = c4.data();
@@ -142,8 +151,8 @@ extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *con
     const size_t smem = ts.max_smem;
 #define RUN(K, T)                                                      \
     do {                                                               \
-        if (unit) run_grid<K, T, true>(a, ts.ntiles, smem);            \
-        else run_grid<K, T, false>(a, ts.ntiles, smem);                \
+        if (unit) run_grid<K, T, true>(a, ts.ntiles, smem, mode);      \
+        else run_grid<K, T, false>(a, ts.ntiles, smem, mode);          \
     } while (0)
     if (threads == 128) { if (kind == POISSON_TRIA) RUN(POISSON_TRIA, 128); else RUN(POISSON_TETRA, 128); }
     else if (threads == 256) { if (kind == POISSON_TRIA) RUN(POISSON_TRIA, 256); else RUN(POISSON_TETRA, 256); }
