@@ -155,3 +155,18 @@ def test_negative_jacobian_flag(emu, input_dir):
     num = D.number(m, S.POISSON_TETRA)
     val, rhs, oval, orhs, stats, nbad = _run(emu, m, S.POISSON_TETRA, num)
     assert nbad == 1 and stats[4] == 1
+
+
+def test_rows_without_elements_and_tiny_meshes(emu):
+    """Free nodes that no element references (empty rows) and meshes smaller than one tile slice."""
+    m = M.gen_tetra(-1, 1, 3, -1, 1, 3, -1, 1, 3)
+    extra = np.array([[5.0, 6.0], [5.0, 6.0], [5.0, 7.0]])             # two stray free nodes, not in any element
+    m.coords = np.ascontiguousarray(np.concatenate([m.coords, extra], axis=1))
+    num = D.number(m, S.POISSON_TETRA)
+    val, rhs, oval, orhs, stats, nbad = _run(emu, m, S.POISSON_TETRA, num, tile_rows=32)
+    assert nbad == 0 and np.array_equal(val, oval) and np.array_equal(rhs, orhs)
+    assert num.size_global == 8 + 2 and rhs[-1] == 0.0 and rhs[-2] == 0.0
+    m = M.gen_tria_poisson(2)                                           # one free node, 8 triangles
+    num = D.number(m, S.POISSON_TRIA)
+    assert num.size_global == 1
+    _check(_run(emu, m, S.POISSON_TRIA, num, tile_rows=32))
