@@ -47,8 +47,9 @@ struct TiledArgs {
 __device__ __forceinline__ void tiled_ld_xyz(const double *p, double &x, double &y, double &z)
 {
 #if defined(__CUDA_ARCH__)
-    double w;
+    double w;                                                // the pad lane of the 256-bit load
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+    (void)w;
 #else
     x = p[0]; y = p[1]; z = p[2];
 #endif
@@ -181,7 +182,7 @@ template <int KIND, int THREADS, int MINB, bool UNIT>
 __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled_kernel(const TiledArgs a)
 {
     using T = ElemTraits<KIND>;
-    constexpr int NPE = T::NPE, NDIM = T::NDIM, NSIZE = NPE;
+    constexpr int NPE = T::NPE, NSIZE = NPE;
     static_assert(T::NDOF == 1, "tiled value pass: one dof per node");
     constexpr int NWARPS = THREADS / 32;
 
@@ -309,9 +310,9 @@ __global__ void __launch_bounds__(THREADS, MINB) assemble_tiled2_kernel(const Ti
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int *td = a.tdesc + (size_t)blockIdx.x * TILE_DESC_INTS;
     const int row_off = td[TD_ROW_OFF], nrows_pad = td[TD_NROWS_PAD], el_off = td[TD_EL_OFF], nel = td[TD_NEL];
-    const int slice0 = td[TD_SLICE0], nnz = td[TD_NNZ], crec_off = td[TD2_CREC_OFF], cbuf = td[TD2_CBUF];
+    const int slice0 = td[TD_SLICE0], crec_off = td[TD2_CREC_OFF], cbuf = td[TD2_CBUF];
     double *Cb = reinterpret_cast<double *>(smem_raw);       // [cbuf]: run-ordered contributions
-    double *acc = Cb + cbuf;                                 // [nnz] : the tile's CSR values, tile-row order
+    double *acc = Cb + cbuf;                                 // [td[TD_NNZ]]: the tile's CSR values, tile-row order
 
     // the row threads' descriptors and first run-length chunk: issued now, consumed in phase B
     int4 my_tr = make_int4(-1, 0, 0, 0), my_s2 = make_int4(0, 0, 0, 0);
