@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "cuda_shim.h"
+#include "emu_formats.hpp"
 
 thread_local uint3 threadIdx, blockIdx;
 uint3 blockDim, gridDim;
@@ -59,56 +60,12 @@ extern "C" int emu_assemble_tiled(int kind, int nElem, int nNode, const int *con
     if (kind != POISSON_TRIA && kind != POISSON_TETRA) return 2;
     const bool build_only = threads < 0;          // tile statistics only (large meshes: the emulated kernel is slow)
     if (build_only) threads = -threads;
-    const int npe = kind == POISSON_TRIA ? 3 : 4, nsize = npe, ndim = kind == POISSON_TRIA ? 2 : 3;
-    const int rec_ints = ((npe + nsize + 3) / 4) * 4, stride = ndim == 3 ? 4 : 2;
-    // --- device formats, restated (pattern.cu: pack_conn/pack_dof, pack_xyz, conn4, inc sort, fill_asm_inc) ---
-    std::vector<int> erec((size_t)nElem * rec_ints, -1), conn4((size_t)nElem * 4);
-    for (int e = 0; e < nElem; e++) {
-        for (int i = 0; i < npe; i++) erec[(size_t)e * rec_ints + i] = conn0[(size_t)i * nElem + e];
-        for (int k = 0; k < nsize; k++) erec[(size_t)e * rec_ints + npe + k] = edof[(size_t)k * nElem + e];
-        for (int i = 0; i < 4; i++) conn4[(size_t)e * 4 + i] = conn0[(size_t)(i < npe ? i : npe - 1) * nElem + e];
-    }
-    std::vector<double> xyz((size_t)nNode * stride, 0.0);
-    for (int n = 0; n < nNode; n++)
-        for (int d = 0; d < ndim; d++) xyz[(size_t)n * stride + d] = xyz_soa[(size_t)d * nNode + n];
-    std::vector<int> rinc_ptr(nloc + 1, 0);
-    for (int e = 0; e < nElem; e++)
-        for (int k = 0; k < nsize; k++) {
-            const int d = edof[(size_t)k * nElem + e];
-            if (d >= row_lo && d < row_lo + nloc) rinc_ptr[d - row_lo + 1]++;
-        }
-    for (int r = 0; r < nloc; r++) rinc_ptr[r + 1] += rinc_ptr[r];
-    std::vector<int> rinc(rinc_ptr[nloc] > 0 ? rinc_ptr[nloc] : 1), cur(rinc_ptr.begin(), rinc_ptr.end() - 1);
-    for (int e = 0; e < nElem; e++)
-        for (int k = 0; k < nsize; k++) {
-            const int d = edof[(size_t)k * nElem + e];
-            if (d >= row_lo && d < row_lo + nloc) rinc[cur[d - row_lo]++] = e * nsize + k;
-        }
-    const int nslices = (nloc + 31) / 32;
-    std::vector<long long> ainc_off(nslices + 1, 0);
-    for (int s = 0; s < nslices; s++) {
-        int w = 0;
-        for (int l = 0; l < 32 && s * 32 + l < nloc; l++) w = std::max(w, rinc_ptr[s * 32 + l + 1] - rinc_ptr[s * 32 + l]);
-        ainc_off[s + 1] = ainc_off[s] + (long long)w * 32;
-    }
-    std::vector<int> ainc((size_t)ainc_off[nslices] * 2 + 2, -1);
-    for (int r = 0; r < nloc; r++) {
-        const int c0 = rowptr[r], len = rowptr[r + 1] - c0;
-        int m = 0;
-        for (int q = rinc_ptr[r]; q < rinc_ptr[r + 1]; q++, m++) {
-            const int code = rinc[q], e = code / nsize;
-            unsigned int w = 0;
-            for (int j = 0; j < nsize; j++) {
-                const int c = edof[(size_t)j * nElem + e];
-                unsigned int sl = 255u;
-                if (c >= 0) sl = (unsigned int)(std::lower_bound(col + c0, col + c0 + len, c) - (col + c0));
-                w |= (sl & 255u) << (8 * j);
-            }
-            int *out = ainc.data() + (size_t)(ainc_off[r >> 5] + (r & 31) + (long long)m * 32) * 2;
-            out[0] = code;
-            out[1] = (int)w;
-        }
-    }
+    EmuFormats F;
+    emu_build_formats(kind, nElem, nNode, conn0, edof, xyz_soa, row_lo, nloc, rowptr, col, F);
+    const int npe = F.npe, nsize = F.nsize, ndim = F.ndim, rec_ints = F.rec_ints, stride = F.stride;
+    std::vector<int> &erec = F.erec, &conn4 = F.conn4, &rinc_ptr = F.rinc_ptr, &rinc = F.rinc, &ainc = F.ainc;
+    std::vector<long long> &ainc_off = F.ainc_off;
+    std::vector<double> &xyz = F.xyz;
     // --- the product's tile builder ---
     TileInput in;
     in.nloc = nloc; in.row_lo = row_lo; in.nElem = nElem; in.npe = npe; in.nsize = nsize; in.rec_ints = rec_ints;
