@@ -2,6 +2,7 @@
 //
 // Same command line as the Fortran executables (bin/makefile:4-11), plus the physics selector:
 //     pfem_driver <triapoisson|tetrapoisson|triaelasticity|tetraelasticity> nodes.dat elems.dat DirichBC.dat [ForceBC.dat]
+//     pfem_driver <physics> mesh.pfemb        (one binary container of the same arrays: csrc/host_meshio.cu)
 // and the same flow (tetrapoissonparallelimpl1.F): read the three text files (:216-355), number the DOFs (:357-367),
 // partition with METIS and renumber when more than one rank runs (:423-677), build ElemDofArray (:698-713),
 // initialise the solver (:759-779), pattern pass (:791-802), setZero (:817), value pass (:828-884, one batched call),
@@ -9,14 +10,13 @@
 // Ranks: one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK come from the launcher (torchrun --no-python works);
 // rank 0 passes the NCCL id to the others through the file named by PFEM_NCCL_ID_FILE (the MPI_Bcast of a real driver).
 // Options in place of petsc_options.dat: PFEM_KSP_RTOL (default 1e-5, PETSc's), PFEM_KSP_MAX_IT.
+// PFEM_WRITE_PFEMB=<file> saves the parsed input as a binary container.
 #include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
-#include <sstream>
 #include <string>
 #include <vector>
 
@@ -33,6 +33,13 @@ void pfem_host_elem_dof_array(int nElem, int npElem, int ndof, int nNode, const 
                               int *elemDof);
 int pfem_host_select_elements(int nElem, int nsize, const int *elemDof, int row_lo, int row_hi, int *list);
 void pfem_host_gather_rows(int nElem, int ncol, const int *in, int nsel, const int *list, int *out);
+long long pfem_host_read_table(const char *path, int ncols, double *out, long long nrows_cap);
+int pfem_host_mesh_read_binary_header(const char *path, long long sizes[6]);
+int pfem_host_mesh_read_binary(const char *path, double *coords, int *conn, int *dbc_node, int *dbc_dof, double *dbc_val,
+                               int *fbc_node, int *fbc_dof, double *fbc_val);
+int pfem_host_mesh_write_binary(const char *path, int ndim, int npElem, int nNode, int nElem, const double *coords,
+                                const int *conn, int nDBC, const int *dbc_node, const int *dbc_dof, const double *dbc_val,
+                                int nFBC, const int *fbc_node, const int *fbc_dof, const double *fbc_val);
 }
 
 #define CHECK(call)                                                                     \
@@ -44,27 +51,20 @@ void pfem_host_gather_rows(int nElem, int ncol, const int *in, int nsel, const i
         }                                                                               \
     } while (0)
 
-static bool read_table(const char *path, int ncols, std::vector<std::vector<double>> &cols)
+// one text table of the reference's input format, column-major (one pass over the file: pfem_host_read_table)
+static bool read_table(const char *path, int ncols, std::vector<double> &tab, long long &nrows)
 {
-    std::ifstream f(path);
-    if (!f) { fprintf(stderr, "File ... %s does not exist\n", path); return false; }
-    cols.assign(ncols, {});
-    std::string line;
-    while (std::getline(f, line)) {
-        std::istringstream ss(line);
-        std::vector<double> v;
-        double x;
-        while (ss >> x) v.push_back(x);
-        if ((int)v.size() < ncols) continue;
-        for (int c = 0; c < ncols; c++) cols[c].push_back(v[c]);
-    }
-    return true;
+    nrows = pfem_host_read_table(path, ncols, nullptr, 0);
+    if (nrows < 0) { fprintf(stderr, "%s\n", pfem_last_error()); return false; }
+    tab.assign((size_t)ncols * (nrows > 0 ? nrows : 1), 0.0);
+    return pfem_host_read_table(path, ncols, tab.data(), nrows) == nrows;
 }
 
 int main(int argc, char **argv)
 {
-    if (argc < 5) {
-        fprintf(stderr, "usage: %s <triapoisson|tetrapoisson|triaelasticity|tetraelasticity> nodes elems DirichBC [ForceBC]\n", argv[0]);
+    if (argc < 3) {
+        fprintf(stderr, "usage: %s <triapoisson|tetrapoisson|triaelasticity|tetraelasticity> nodes elems DirichBC [ForceBC]\n"
+                        "   or: %s <physics> mesh.pfemb      (binary container of the same arrays, tools/mesh_convert.py)\n", argv[0], argv[0]);
         return 1;
     }
     const std::string phys = argv[1];
@@ -79,26 +79,44 @@ int main(int argc, char **argv)
     const int device = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : 0;
     const int nsize = npElem * ndof;
 
-    // ---- read the input files ----
-    std::vector<std::vector<double>> t;
-    if (!read_table(argv[2], 1 + ndim, t)) return 1;
-    const int nNode = (int)t[0].size();
-    std::vector<double> coords((size_t)ndim * nNode);
-    for (int c = 0; c < ndim; c++) std::copy(t[1 + c].begin(), t[1 + c].end(), coords.begin() + (size_t)c * nNode);
-    if (!read_table(argv[3], 1 + npElem, t)) return 1;
-    const int nElem = (int)t[0].size();
-    std::vector<int> conn((size_t)npElem * nElem);
-    for (int i = 0; i < npElem; i++)
-        for (int e = 0; e < nElem; e++) conn[(size_t)i * nElem + e] = (int)t[1 + i][e];
-    if (!read_table(argv[4], 3, t)) return 1;
-    const int nDBC = (int)t[0].size();
-    std::vector<int> dbc_node(nDBC), dbc_dof(nDBC);
-    std::vector<double> dbc_val(nDBC);
-    for (int b = 0; b < nDBC; b++) { dbc_node[b] = (int)t[0][b]; dbc_dof[b] = (int)t[1][b]; dbc_val[b] = t[2][b]; }
-    std::vector<int> fbc_node, fbc_dof;
-    std::vector<double> fbc_val;
-    if (argc >= 6 && read_table(argv[5], 3, t))
-        for (size_t b = 0; b < t[0].size(); b++) { fbc_node.push_back((int)t[0][b]); fbc_dof.push_back((int)t[1][b]); fbc_val.push_back(t[2][b]); }
+    // ---- read the input: the reference's three (four) text tables, or one .pfemb container holding the same arrays ----
+    int nNode = 0, nElem = 0, nDBC = 0;
+    std::vector<double> coords, dbc_val, fbc_val;
+    std::vector<int> conn, dbc_node, dbc_dof, fbc_node, fbc_dof;
+    const size_t l2 = strlen(argv[2]);
+    if (l2 > 6 && !strcmp(argv[2] + l2 - 6, ".pfemb")) {
+        long long sz[6];
+        CHECK(pfem_host_mesh_read_binary_header(argv[2], sz));
+        if (sz[0] != ndim || sz[1] != npElem) { fprintf(stderr, "%s holds a %lldD mesh with %lld nodes per element\n", argv[2], sz[0], sz[1]); return 1; }
+        nNode = (int)sz[2]; nElem = (int)sz[3]; nDBC = (int)sz[4];
+        coords.resize((size_t)ndim * nNode); conn.resize((size_t)npElem * nElem);
+        dbc_node.resize(nDBC); dbc_dof.resize(nDBC); dbc_val.resize(nDBC);
+        fbc_node.resize(sz[5]); fbc_dof.resize(sz[5]); fbc_val.resize(sz[5]);
+        CHECK(pfem_host_mesh_read_binary(argv[2], coords.data(), conn.data(), dbc_node.data(), dbc_dof.data(), dbc_val.data(),
+                                         fbc_node.data(), fbc_dof.data(), fbc_val.data()));
+    } else {
+        if (argc < 5) { fprintf(stderr, "text input needs nodes, elems and DirichBC files\n"); return 1; }
+        std::vector<double> t;
+        long long n = 0;
+        if (!read_table(argv[2], 1 + ndim, t, n)) return 1;
+        nNode = (int)n;
+        coords.assign(t.begin() + n, t.begin() + n * (1 + ndim));                     // columns 1..ndim (column 0 is the id)
+        if (!read_table(argv[3], 1 + npElem, t, n)) return 1;
+        nElem = (int)n;
+        conn.resize((size_t)npElem * nElem);
+        for (size_t q = 0; q < conn.size(); q++) conn[q] = (int)t[(size_t)n + q];
+        if (!read_table(argv[4], 3, t, n)) return 1;
+        nDBC = (int)n;
+        dbc_node.resize(nDBC); dbc_dof.resize(nDBC); dbc_val.resize(nDBC);
+        for (int b = 0; b < nDBC; b++) { dbc_node[b] = (int)t[b]; dbc_dof[b] = (int)t[(size_t)n + b]; dbc_val[b] = t[2 * (size_t)n + b]; }
+        if (argc >= 6 && read_table(argv[5], 3, t, n))
+            for (long long b = 0; b < n; b++) { fbc_node.push_back((int)t[b]); fbc_dof.push_back((int)t[(size_t)n + b]); fbc_val.push_back(t[2 * (size_t)n + b]); }
+    }
+    // PFEM_WRITE_PFEMB=<file>: save what was just read as a binary container (text -> binary conversion by the driver itself)
+    if (rank == 0 && getenv("PFEM_WRITE_PFEMB"))
+        CHECK(pfem_host_mesh_write_binary(getenv("PFEM_WRITE_PFEMB"), ndim, npElem, nNode, nElem, coords.data(), conn.data(), nDBC,
+                                          dbc_node.data(), dbc_dof.data(), dbc_val.data(), (int)fbc_node.size(), fbc_node.data(),
+                                          fbc_dof.data(), fbc_val.data()));
     if (rank == 0) printf(" nElem_global = %d\n nNode_global = %d\n npElem = %d\n ndof = %d\n", nElem, nNode, npElem, ndof);
 
     // ---- partition (every rank computes the same METIS partition: deterministic, replaces the MPI_Bcast) ----

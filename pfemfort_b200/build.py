@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
 NO_FMA = {"elements.cu", "assembly.cu", "assembly_tiled.cu"}
 # host-side set-up loops (tile construction) use OpenMP
 OPENMP = {"assembly_tiled.cu"}
-SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "cg.cu", "comm.cu", "host_driver.cu"]
+SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "cg.cu", "comm.cu", "host_driver.cu", "host_meshio.cu"]
 
 
 def _nvcc() -> str:

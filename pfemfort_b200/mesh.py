@@ -50,7 +50,23 @@ def _open(path: str):
     return gzip.open(path, "rt") if path.endswith(".gz") else open(path, "rt")
 
 
-def _load_table(path: str) -> np.ndarray:
+def _load_table(path: str, ncols: int | None = None) -> np.ndarray:
+    """One text table ``id v1 v2 ...``.  Plain files go through the one-pass C parser of the library
+    (csrc/host_meshio.cu) when the column count is known; gzipped fixtures through numpy."""
+    if ncols is not None and not path.endswith(".gz"):
+        import ctypes as C
+
+        from . import solver as S
+        lib = S.load_library()
+        lib.pfem_host_read_table.restype = C.c_longlong
+        lib.pfem_host_read_table.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_longlong]
+        n = lib.pfem_host_read_table(path.encode(), ncols, None, 0)
+        if n < 0:
+            raise FileNotFoundError(path)
+        out = np.zeros((ncols, max(n, 1)))
+        # the count pass tokenises, the fill pass converts: rows with non-numeric tokens drop out in the second pass only
+        n = min(n, lib.pfem_host_read_table(path.encode(), ncols, out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return np.ascontiguousarray(out[:, :n].T)
     with _open(path) as f:
         return np.loadtxt(f, dtype=np.float64, ndmin=2)
 
@@ -196,3 +212,46 @@ def gen_tetra(x0, x1, nEx, y0, y1, nEy, z0, z1, nEz, dbc: str = "poisson", ndof:
 def exact_poisson_tria(x: np.ndarray, y: np.ndarray) -> np.ndarray:
     """Analytic Laplace solution left in the comments of triapoissonparallelimpl1.F:954-955."""
     return (np.cosh(np.pi * y) - np.sinh(np.pi * y) / np.tanh(np.pi)) * np.sin(np.pi * x)
+
+
+# ---- binary container (.pfemb): the arrays the drivers build from the text files, parsed once -----------------------
+PFEMB_MAGIC = b"PFEMB1\0\0"
+
+
+def write_binary(m: Mesh, path: str) -> None:
+    """Write the PFEMB1 container (layout: csrc/host_meshio.cu).  Little endian, SoA arrays as the drivers hold them."""
+    def i32(a):
+        b = np.ascontiguousarray(a, "<i4").tobytes()
+        return b + (b"\0\0\0\0" if (len(b) // 4) % 2 else b"")
+    with open(path, "wb") as f:
+        f.write(PFEMB_MAGIC)
+        f.write(np.array([m.ndim, m.npElem, m.nNode, m.nElem, m.dbc_node.size, m.fbc_node.size], "<i8").tobytes())
+        f.write(np.ascontiguousarray(m.coords, "<f8").tobytes())
+        f.write(i32(m.conn))
+        f.write(i32(m.dbc_node)); f.write(i32(m.dbc_dof)); f.write(np.ascontiguousarray(m.dbc_val, "<f8").tobytes())
+        f.write(i32(m.fbc_node)); f.write(i32(m.fbc_dof)); f.write(np.ascontiguousarray(m.fbc_val, "<f8").tobytes())
+
+
+def read_binary(path: str) -> Mesh:
+    """Read a PFEMB1 container (memory-mapped: no parsing, no copy until the arrays are used)."""
+    raw = np.memmap(path, dtype=np.uint8, mode="r")
+    if raw.size < 56 or bytes(raw[:8]) != PFEMB_MAGIC:
+        raise ValueError(f"{path} is not a PFEMB1 mesh container")
+    ndim, npe, nN, nE, nD, nF = (int(v) for v in np.frombuffer(raw[8:56], "<i8"))
+    off = 56
+
+    def take(dtype, count, shape=None):
+        nonlocal off
+        nbytes = count * np.dtype(dtype).itemsize
+        a = np.frombuffer(raw[off:off + nbytes], dtype)
+        off += nbytes + (4 if (np.dtype(dtype).itemsize == 4 and count % 2) else 0)
+        return a.reshape(shape) if shape else a
+
+    coords = take("<f8", ndim * nN, (ndim, nN))
+    conn = take("<i4", npe * nE, (npe, nE))
+    dn, dd, dv = take("<i4", nD), take("<i4", nD), take("<f8", nD)
+    fn, fd, fv = take("<i4", nF), take("<i4", nF), take("<f8", nF)
+    if off != raw.size:
+        raise ValueError(f"{path}: size does not match its header")
+    return Mesh(np.array(coords), np.array(conn), np.array(dn), np.array(dd), np.array(dv), np.array(fn), np.array(fd),
+                np.array(fv), name=os.path.basename(path))

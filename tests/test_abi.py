@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
 def test_host_side_exports():
     lib = S.load_library()
     for n in ("pfem_host_partition_mesh", "pfem_host_number_dofs", "pfem_host_renumber_conn", "pfem_host_elem_dof_array",
-              "pfem_host_select_elements", "pfem_host_gather_rows"):
+              "pfem_host_select_elements", "pfem_host_gather_rows", "pfem_host_read_table", "pfem_host_mesh_read_binary_header",
+              "pfem_host_mesh_read_binary", "pfem_host_mesh_write_binary"):
         assert hasattr(lib, n)
 
 
