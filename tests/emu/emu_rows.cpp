@@ -3,6 +3,7 @@
 // through tests/emu/cuda_shim.h, for all four element kinds.  tests/test_rows_emu.py compares the CSR values / RHS bit
 // for bit with the oracle.  The product never loads this.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -22,9 +23,10 @@ using namespace pfem;
 template <class Kernel>
 static void run_grid(Kernel kernel, int nblocks, int threads, size_t smem_bytes)
 {
-    std::vector<unsigned char> smem(smem_bytes + 64);
-    unsigned char *base = smem.data();
-    base += (16 - ((uintptr_t)base & 15)) & 15;
+    // exactly smem_bytes, 16-byte aligned: an overrun of the CTA's shared memory is a heap overflow AddressSanitizer sees
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 16, smem_bytes ? smem_bytes : 16) != 0) return;
+    unsigned char *base = static_cast<unsigned char *>(raw);
     emu_smem = base;
     std::memset(base, 0xFF, smem_bytes);          // NaN poison
     emu_barrier.reset(threads);
@@ -43,6 +45,7 @@ static void run_grid(Kernel kernel, int nblocks, int threads, size_t smem_bytes)
             }
         });
     for (auto &th : pool) th.join();
+    free(raw);
 }
 
 template <int KIND, int R>

@@ -6,6 +6,7 @@
 // same build_tiles() the product calls, and then executes the very same kernel source.  tests/test_tiled_emu.py
 // compares the resulting CSR values / RHS bit for bit with the oracle.  Built by that test with g++.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -25,9 +26,10 @@ using namespace pfem;
 template <int KIND, int THREADS, bool UNIT>
 static void run_grid(const TiledArgs &args, int ntiles, size_t smem_bytes, int mode)
 {
-    std::vector<unsigned char> smem(smem_bytes + 64);
-    unsigned char *base = smem.data();
-    base += (16 - ((uintptr_t)base & 15)) & 15;
+    // exactly smem_bytes, 16-byte aligned: an overrun of the CTA's shared memory is a heap overflow AddressSanitizer sees
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 16, smem_bytes ? smem_bytes : 16) != 0) return;
+    unsigned char *base = static_cast<unsigned char *>(raw);
     emu_smem = base;
     std::memset(base, 0xFF, smem_bytes);          // NaN poison: a read of unstaged data shows up in the results
     emu_barrier.reset(THREADS);
@@ -47,6 +49,7 @@ static void run_grid(const TiledArgs &args, int ntiles, size_t smem_bytes, int m
             }
         });
     for (auto &th : pool) th.join();
+    free(raw);
 }
 
 // conn0: [npe][nElem] 0-based NEW node ids; edof: [nsize][nElem] global dof ids (-1 Dirichlet); xyz: [ndim][nNode] NEW
