@@ -54,10 +54,16 @@ struct EmuBarrier {
 };
 extern EmuBarrier emu_barrier;
 extern unsigned char *emu_smem;
+#ifdef PFEM_EMU_BREAK_SYNC          // negative control for the ThreadSanitizer run: barriers removed, races must be reported
+static inline void __syncthreads() {}
+#else
 static inline void __syncthreads() { emu_barrier.wait(); }
+#endif
 #define PFEM_DYN_SMEM(name) unsigned char *name = emu_smem
 
 // Sanitizer run (not part of the default suite; needs LD_PRELOAD of libasan):
 //   g++ -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer ... (same flags as tests/test_*_emu.py) -o tests/emu/_build/libemu_X.so
 //   ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest tests/test_tiled_emu.py tests/test_rows_emu.py
 // The CTA's shared memory is an exact-size heap block, so shared-memory overruns are caught as well as global ones.
+// Race detection: the same with -fsanitize=thread and libtsan.so (CUDA threads are OS threads, __syncthreads is a real
+// barrier, so a missing barrier is a data race ThreadSanitizer reports; -DPFEM_EMU_BREAK_SYNC is the negative control).
