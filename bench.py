@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of the PFEMFort implicit hot path on B200.
 
-Workload (BASELINE.json configs[4], the configuration `metric` is quoted on): 3-D Poisson on the genTetra
-200x200x200x6 = 48 M P1-tet mesh over [-1,1]^3, u = x^2+y^2+z^2 on the boundary, source -6, Jacobi-CG to
-rtol 1e-10 (reference run with -ksp_type cg -pc_type jacobi -ksp_rtol 1e-10).  Synthetic inputs generated on
-the box by the reference's own recipe (pfemfort_b200/mesh.py).
+Default workload = BASELINE.json configs[4] (the configuration `metric` is quoted on): 3-D Poisson on the genTetra
+200x200x200x6 = 48 M P1-tet mesh over [-1,1]^3, u = x^2+y^2+z^2 on the boundary, source -6, Jacobi-CG to rtol 1e-10
+(reference run with -ksp_type cg -pc_type jacobi -ksp_rtol 1e-10).  `--workload c2|c3|c4|c5` selects the other
+BASELINE configurations (c2 tria1000x1000 Poisson, c3 beam3Dtet6366 elasticity fixture with its ForceBC file,
+c4 beam 50x300x50x6 elasticity).  Synthetic inputs are generated on the box by the reference's own recipes
+(pfemfort_b200/mesh.py); c3 reads the bundled fixture under tests/golden/input.
 
-One "step" = one pass of the hot path: setZero -> fused value pass (Ke/Fe + assembly + lifting) -> Jacobi-CG
-solve to tolerance.  `value` (CG DOF-iter/s = N_free * iterations / solve seconds, whole job over all ranks)
-is measured with the mesh, pattern and applied values already resident in HBM; `assembly` carries the second
-half of the metric (Melem/s).  `e2e` is the same metric through the C ABI from HOST buffers: mesh upload,
-pattern pass, value pass, solve and the read-back of the solution are all inside its timed region.
+One "step" = one pass of the hot path: setZero -> fused value pass (Ke/Fe + assembly + lifting) [-> ForceBC adds]
+-> Jacobi-CG solve to tolerance.  `value` (CG DOF-iter/s = N_free * iterations / solve seconds, whole job over all
+ranks) is measured with the mesh, pattern and applied values already resident in HBM; `assembly` carries the second
+half of the metric (Melem/s).  `e2e` is the same metric through the C ABI from HOST buffers: mesh upload, pattern
+pass, value pass, solve and the read-back of the solution are all inside its timed region.  `parity` compares the
+GPU's assembled values / RHS / iteration count with the CPU oracle in the same run (N = 1: on the benchmark's own
+system; N > 1: per-rank row blocks of a mid-size mesh, untimed, before the timed region).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cells 200]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c5] [--cells n]
 
 For N > 1 launch with torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 """
@@ -33,6 +37,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 RTOL = 1e-10
+TUNING_ENV = ("PFEM_ASM", "PFEM_CG", "PFEM_CG_SR", "PFEM_PCG_CFG", "PFEM_PCG_FUSED", "PFEM_KERNELS_P2P", "PFEM_TILE_ROWS",
+              "PFEM_TILE_THREADS", "PFEM_SYNC", "PFEM_ARITH")
 
 
 def parse():
@@ -41,13 +47,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells", type=int, default=200, help="cells per side of the genTetra cube (200 = 48 M tets)")
+    ap.add_argument("--workload", default="c5", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--cells", type=int, default=0, help="size override: cells per side (c5: 200, c4: 50, c2: 1000)")
     ap.add_argument("--partition", default="metis", choices=["metis", "slab"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-elems", type=int, default=48_000_000, help="elements in the CPU assembly sample")
-    ap.add_argument("--cpu-its", type=int, default=100, help="CG iterations in the CPU solve sample")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--cpu-elems", type=int, default=0, help="elements in the CPU assembly sample (0 = all)")
+    ap.add_argument("--cpu-its", type=int, default=-1,
+                    help="CG iterations in the CPU solve sample (-1 = workload default; 0 = solve to tolerance)")
     return ap.parse_args()
+
+
+def host_threads() -> int:
+    """Host threads of the CPU arm: every core this process may run on, regardless of OMP_NUM_THREADS
+    (torchrun exports OMP_NUM_THREADS=1, which must not shrink the reference arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 def measured_peak():
@@ -58,12 +76,29 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(nElem, nNode, N, nnz, nDBC):
+def algorithmic_bytes(npe, nsize, ndim, nElem, nNode, N, nnz, nDBC):
     """compulsory traffic, int32 indices, FP64 values."""
-    asm = 16 * nElem + 16 * nElem + 8 * 3 * nNode + 12 * nnz + 4 * N + 8 * N + 8 * nDBC
+    asm = 4 * npe * nElem + 4 * nsize * nElem + 8 * ndim * nNode + 12 * nnz + 4 * N + 8 * N + 8 * nDBC
     spmv = 12 * nnz + 4 * (N + 1) + 16 * N
     cg_iter = 12 * nnz + 4 * (N + 1) + 104 * N
     return asm, spmv, cg_iter
+
+
+def captured_traffic(kernel: str, workload: str, n_gpus: int):
+    """dram__bytes_read+write per launch of `kernel` from a committed `ncu --set full` capture (profiles/traffic.json,
+    written by tools/ncu_traffic.py from the .ncu-rep), or None: never a number that does not belong to this build /
+    workload / tuning."""
+    if any(os.environ.get(k) for k in TUNING_ENV):
+        return None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tab = json.load(f)
+        for rec in tab:
+            if rec["workload"] == workload and rec["n_gpus"] == n_gpus and rec["kernel"] in kernel:
+                return rec, rec.get("source")
+    except Exception:
+        pass
+    return None, None
 
 
 class ClockSampler:
@@ -109,70 +144,133 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(cells, nparts, partition, rank, bcast):
-    from pfemfort_b200 import driver as D, mesh as M, solver as S
-    m = M.gen_tetra(-1.0, 1.0, cells, -1.0, 1.0, cells, -1.0, 1.0, cells)
-    npart = None
-    if nparts > 1:
-        if partition == "slab":
-            # plane-wise slabs in z: a valid node partition (partition vectors are inputs to the hot path)
-            nn = (cells + 1) * (cells + 1)
-            k = np.arange(m.nNode, dtype=np.int64) // nn
-            npart = (k * nparts // (cells + 1)).astype(np.int32)
-        else:
-            npart = np.zeros(m.nNode, np.int32)
-            if rank == 0:      # rank 0 partitions, everyone receives (tetrapoissonparallelimpl1.F:457-484)
-                _, npart = D.partition(m, S.POISSON_TETRA, nparts)
-            npart = bcast(npart)
-    num = D.number(m, S.POISSON_TETRA, nparts, npart)
-    return m, num
+# ---- workloads (BASELINE.json configs[1..4]) ----------------------------------------------------------------------
+
+def make_workload(name: str, cells: int):
+    """-> dict(mesh, kind, label, max_it, cpu_its): the inputs of one BASELINE configuration, by the reference's recipes."""
+    from pfemfort_b200 import mesh as M, solver as S
+    if name == "c5":
+        n = cells or 200
+        m = M.gen_tetra(-1.0, 1.0, n, -1.0, 1.0, n, -1.0, 1.0, n)
+        return dict(mesh=m, kind=S.POISSON_TETRA, max_it=100000, cpu_its=0, n=n,
+                    label=f"genTetra {n}^3 x6 P1-tet Poisson on [-1,1]^3, Jacobi-CG rtol {RTOL:g}")
+    if name == "c4":
+        n = cells or 50
+        m = M.gen_tetra(-0.5, 0.5, n, 0.0, 6.0, 6 * n, -0.5, 0.5, n, dbc="clamp_y0", ndof=3)
+        return dict(mesh=m, kind=S.ELASTICITY_TETRA, max_it=200000, cpu_its=200, n=n,
+                    label=f"genTetra beam {n}x{6 * n}x{n} x6 P1-tet linear elasticity, clamped at y=0, Jacobi-CG rtol {RTOL:g}")
+    if name == "c3":
+        m = M.read_mesh(os.path.join(ROOT, "tests", "golden", "input", "beam3Dtet6366"), swap_34=True)
+        return dict(mesh=m, kind=S.ELASTICITY_TETRA, max_it=100000, cpu_its=0, n=0,
+                    label=f"beam3Dtet6366 fixture (local nodes 3<->4 swapped) P1-tet linear elasticity + ForceBC, Jacobi-CG rtol {RTOL:g}")
+    n = cells or 1000
+    m = M.gen_tria_poisson(n)
+    return dict(mesh=m, kind=S.POISSON_TRIA, max_it=100000, cpu_its=0, n=n,
+                label=f"tria{n}x{n} P1 Poisson on the unit square, Jacobi-CG rtol {RTOL:g}")
+
+
+def node_partition(w, nparts, how, rank, bcast):
+    from pfemfort_b200 import driver as D
+    m = w["mesh"]
+    if nparts <= 1:
+        return None
+    if how == "slab" and w["n"]:
+        # slabs of whole node planes (rows in 2-D) along the slowest axis: a valid node partition (partition vectors
+        # are inputs to the hot path)
+        planes = w["n"] + 1
+        nn = m.nNode // planes
+        k = np.arange(m.nNode, dtype=np.int64) // nn
+        return (k * nparts // planes).astype(np.int32)
+    npart = np.zeros(m.nNode, np.int32)
+    if rank == 0:      # rank 0 partitions, everyone receives (tetrapoissonparallelimpl1.F:457-484)
+        _, npart = D.partition(m, w["kind"], nparts)
+    return bcast(np.ascontiguousarray(npart, np.int32))
+
+
+def force_bc(w, num):
+    from pfemfort_b200 import driver as D, solver as S
+    m = w["mesh"]
+    if not m.fbc_node.size:
+        return [], []
+    return D.force_bc_rows(m, num, S.KIND_DIMS[w["kind"]][1])
+
+
+def diff_stats(a, b):
+    """max|a-b| relative to max|b| (norm-wise), and the count of bitwise-different entries"""
+    if a.size == 0:
+        return 0.0, 0
+    scale = float(np.abs(b).max()) or 1.0
+    d = 0.0
+    nd = 0
+    step = 1 << 24
+    for i in range(0, a.size, step):
+        x, y = a[i:i + step], b[i:i + step]
+        d = max(d, float(np.abs(x - y).max()))
+        nd += int(np.count_nonzero(x != y))
+    return d / scale, nd
+
+
+def oracle_system(w, num, threads, elem_mask=None, val=None, rhs=None, rp=None, col=None):
+    """The CPU oracle's assembled system for a workload (pattern unless given, value pass, ForceBC adds)."""
+    from oracle import pyoracle as O
+    from pfemfort_b200 import driver as D
+    m, kind = w["mesh"], w["kind"]
+    if rp is None:
+        rp, col = O.pattern(num.elemDof, num.size_global)
+    old = num.node_map_get_old if num.nparts > 1 else None
+    val, rhs, nbad = O.assemble(kind, num.conn_new, m.coords, old, num.elemDof, num.solnApplied, D.DEFAULT_ELEMDATA[kind],
+                                D.DEFAULT_TIMEDATA, rp, col, elem_mask=elem_mask, threads=threads, val=val, rhs=rhs)
+    rows, vals = force_bc(w, num)
+    for r, v in zip(rows, vals):
+        rhs[r] += v
+    return rp, col, val, rhs
 
 
 def run_reference(args, rank, world):
-    """The reference arm: the CPU restatement of the PETSc/MPI path (oracle/pfem_oracle.c, OpenMP) on the host
-    cores.  PETSc, MPI and a Fortran compiler are absent here and on the GPU box, so oracle/_ref cannot exist;
-    kind = "port".  Each step = a bounded sample: value pass over the first `cpu_elems` elements + `cpu_its`
-    CG iterations on the full system."""
+    """The reference arm: the CPU restatement of the PETSc/MPI path (oracle/pfem_oracle.c, OpenMP) on ALL host cores
+    of the box.  PETSc, MPI and a Fortran compiler are absent here and on the GPU box, so oracle/_ref cannot exist;
+    kind = "port".  Each step = a bounded sample: value pass over the first `cpu_elems` elements + `cpu_its` CG
+    iterations on the full system.  Under torchrun only rank 0 works."""
     if rank != 0:
         return
     from oracle import pyoracle as O
-    from pfemfort_b200 import driver as D, mesh as M, solver as S
-    threads = O.num_threads()
-    m = M.gen_tetra(-1.0, 1.0, args.cells, -1.0, 1.0, args.cells, -1.0, 1.0, args.cells)
-    o = O.number_dofs(m.nNode, 1, m.dbc_node, m.dbc_dof, m.dbc_val)
-    conn_new = m.conn
-    edof = O.elem_dof_array(conn_new, o["NodeDofArrayNew"])
-    N = o["size_global"]
-    rp, col = O.pattern(edof, N)
-    ed, td = D.DEFAULT_ELEMDATA[S.POISSON_TETRA], D.DEFAULT_TIMEDATA
+    from pfemfort_b200 import driver as D
+    threads = host_threads()
+    w = make_workload(args.workload, args.cells)
+    m, kind = w["mesh"], w["kind"]
+    num = D.number(m, kind)
+    N = num.size_global
     # full assembly once (untimed set-up of the CG sample's matrix), threaded
-    val, rhs, _ = O.assemble(O.POISSON_TETRA, conn_new, m.coords, None, edof, o["solnApplied"], ed, td, rp, col, threads=threads)
-    ne = min(args.cpu_elems, m.nElem)
+    rp, col, val, rhs = oracle_system(w, num, threads)
+    ne = min(args.cpu_elems or m.nElem, m.nElem)
+    its_cap = args.cpu_its if args.cpu_its >= 0 else (100 if args.workload in ("c5", "c4") else 0)
     mask = np.zeros(m.nElem, np.uint8)
     mask[:ne] = 1
-    t_asm, t_cg = [], []
+    t_asm, t_cg, its_done = [], [], 0
     for step in range(args.warmup + args.steps):
         v2 = np.zeros_like(val)
         r2 = np.zeros_like(rhs)
         t0 = time.perf_counter()
-        O.assemble(O.POISSON_TETRA, conn_new, m.coords, None, edof, o["solnApplied"], ed, td, rp, col, elem_mask=mask,
-                   threads=threads, val=v2, rhs=r2)
+        O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied, D.DEFAULT_ELEMDATA[kind],
+                   D.DEFAULT_TIMEDATA, rp, col, elem_mask=mask, threads=threads, val=v2, rhs=r2)
         t1 = time.perf_counter()
-        O.cg_jacobi(rp, col, val, rhs, rtol=RTOL, threads=threads, fixed_its=args.cpu_its)
+        _, its_done, _, _ = O.cg_jacobi(rp, col, val, rhs, rtol=RTOL, max_it=w["max_it"], threads=threads, fixed_its=its_cap)
         t2 = time.perf_counter()
         if step >= args.warmup:
             t_asm.append(t1 - t0)
             t_cg.append(t2 - t1)
-    cg_rate = N * args.cpu_its / float(np.mean(t_cg))
+    its_done = its_cap if its_cap else its_done
+    cg_rate = N * its_done / float(np.mean(t_cg))
     asm_rate = ne / float(np.mean(t_asm)) / 1e6
-    sample = f"first {ne} of {m.nElem} elements assembled; {args.cpu_its} CG iterations on the full {N}-DOF system"
+    sample = (f"first {ne} of {m.nElem} elements assembled; {its_done} CG iterations on the full {N}-DOF system"
+              + ("" if its_cap else " (solve to tolerance)"))
     line = {
         "impl": "reference", "metric": "poisson_cg_dof_iter_per_s", "value": cg_rate, "unit": "DOF-iter/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(t_asm) + np.mean(t_cg)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"genTetra {args.cells}^3 x6 P1-tet Poisson on [-1,1]^3, Jacobi-CG rtol {RTOL:g}",
-                   "elements": int(m.nElem), "dof": int(N), "nnz": int(col.size), "timing": "host wall clock (CPU arm)"},
+        "config": {"workload": w["label"], "elements": int(m.nElem), "nodes": int(m.nNode), "dof": int(N), "nnz": int(col.size)},
+        "run": {"timing": "host wall clock (CPU arm)", "threads": threads},
         "assembly": {"metric": "assembly_melem_per_s", "value": asm_rate, "unit": "Melem/s"},
         "cpu_baseline": {"value": cg_rate, "unit": "DOF-iter/s", "cores": threads, "kind": "port", "sample": sample,
                          "assembly_melem_per_s": asm_rate,
@@ -181,6 +279,40 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def multirank_parity(args, rank, world, local_rank, new_id, bcast, gather_max, gather_min):
+    """N > 1: untimed per-rank row-block check on a mid-size mesh of the same kind, against the sequential oracle.
+    Every rank drives its GPU through the C ABI exactly like the timed run (same partitioner, same exchange path)."""
+    from oracle import pyoracle as O
+    from pfemfort_b200 import driver as D, solver as S
+    small = {"c5": ("c5", 24), "c4": ("c4", 6), "c3": ("c3", 0), "c2": ("c2", 96)}[args.workload]
+    w = make_workload(*small)
+    m, kind = w["mesh"], w["kind"]
+    npart = node_partition(w, world, args.partition, rank, bcast)
+    num = D.number(m, kind, world, npart)
+    s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=new_id())
+    info = D.run_rank(s, m, num, rank=rank, rtol=RTOL, max_it=w["max_it"])
+    rp, col, val = s.get_csr()
+    rhs = s.get_rhs()
+    x = s.get_solution()
+    mode = s.assembly_mode()[0]
+    s.free()
+    lo, hi = num.row_range(rank)
+    orp, ocol, oval, orhs = oracle_system(w, num, 1)
+    ox, oits, oreason, _ = O.cg_jacobi(orp, ocol, oval, orhs, rtol=RTOL, max_it=w["max_it"])
+    a, b = int(orp[lo]), int(orp[hi])
+    pat_ok = bool(np.array_equal(rp, orp[lo:hi + 1] - orp[lo]) and np.array_equal(col, ocol[a:b]))
+    scale = float(np.abs(oval).max()) or 1.0
+    dv = float(np.abs(val - oval[a:b]).max()) / scale if pat_ok and b > a else (0.0 if pat_ok else float("inf"))
+    dr = float(np.abs(rhs - orhs[lo:hi]).max()) / (float(np.abs(orhs).max()) or 1.0) if hi > lo else 0.0
+    dx = float(np.abs(x - ox).max()) / (float(np.abs(ox).max()) or 1.0)
+    bit = bool(pat_ok and np.array_equal(val, oval[a:b]) and np.array_equal(rhs, orhs[lo:hi]))
+    return {"mesh": w["label"], "ranks": world, "pattern_equal_all_ranks": bool(gather_min(1.0 if pat_ok else 0.0) > 0.5),
+            "values_max_rel": gather_max(dv), "rhs_max_rel": gather_max(dr), "solution_max_rel": gather_max(dx),
+            "values_bit_identical_all_ranks": bool(gather_min(1.0 if bit else 0.0) > 0.5),
+            "its_gpu": int(info["its"]), "its_oracle": int(oits), "reason_gpu": int(info["reason"]), "reason_oracle": int(oreason),
+            "assembly_mode": mode, "oracle": "sequential (1 thread, reference element order)"}
 
 
 def main():
@@ -201,15 +333,18 @@ def main():
         raise SystemExit("bench.py: no CUDA device; libpfemb200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    nccl_id = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+
+    def new_id():
+        if world == 1:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             idt = torch.frombuffer(bytearray(S.comm_unique_id()), dtype=torch.uint8).clone()
         dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.numpy().tobytes())
+        return bytes(idt.numpy().tobytes())
 
     def bcast(arr):
         if world == 1:
@@ -223,23 +358,27 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(v: float) -> float:
+    def reduce_ranks(v: float, op) -> float:
         if world == 1:
             return v
         t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(v: float) -> float:
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks = lambda v: reduce_ranks(v, dist.ReduceOp.MAX) if world > 1 else v
+    min_over_ranks = lambda v: reduce_ranks(v, dist.ReduceOp.MIN) if world > 1 else v
+    sum_over_ranks = lambda v: reduce_ranks(v, dist.ReduceOp.SUM) if world > 1 else v
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multirank_parity(args, rank, world, local_rank, new_id, bcast, max_over_ranks, min_over_ranks)
 
     t_setup0 = time.perf_counter()
-    m, num = build_workload(args.cells, world, args.partition, rank, bcast)
-    kind = S.POISSON_TETRA
+    w = make_workload(args.workload, args.cells)
+    m, kind = w["mesh"], w["kind"]
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    npart = node_partition(w, world, args.partition, rank, bcast)
+    num = D.number(m, kind, world, npart)
     ed, td = D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA
     lo, hi = num.row_range(rank)
     size_local = hi - lo
@@ -249,6 +388,7 @@ def main():
         node_map = num.node_map_get_old
     else:
         conn, node_map = num.conn_new, None
+    fbc_rows, fbc_vals = force_bc(w, num)
     # pinned host staging of the step inputs (the e2e leg copies from these every step)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     conn_p, coords_p, applied_p = pin(conn), pin(m.coords), pin(num.solnApplied)
@@ -258,7 +398,7 @@ def main():
     h2d_bytes = conn_p.nbytes + nda_p.nbytes + coords_p.nbytes + applied_p.nbytes + (map_p.nbytes if map_p is not None else 0)
     d2h_bytes = xout_p.nbytes
 
-    s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+    s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=new_id())
 
     stage_t = {}
 
@@ -270,7 +410,7 @@ def main():
 
     def upload_and_pattern():
         s.initialise(size_local, num.size_global)
-        s.set_options(rtol=RTOL, max_it=100000, pc_type=S.PC_JACOBI)
+        s.set_options(rtol=RTOL, max_it=w["max_it"], pc_type=S.PC_JACOBI)
         timed("set_mesh", s.set_mesh, kind, conn_p, coords_p, map_p)
         timed("set_pattern", s.set_pattern_nodal, nda_p)     # element dof lists are formed on the GPU
         timed("set_applied", s.set_applied, applied_p)
@@ -278,6 +418,8 @@ def main():
     def hot_step():
         s.setZero()
         s.assemble(ed, td)
+        for r_, v_ in zip(fbc_rows, fbc_vals):               # rows outside this rank's block are skipped by the library
+            s.add_value(r_, v_)
         s.factoriseAndSolve()
         return s.info()
 
@@ -321,29 +463,27 @@ def main():
     nnz_local = nnz.value
     nnz_total = int(sum_over_ranks(float(nnz_local)))
     peak, peak_src = measured_peak()
-    asm_b, spmv_b, cgit_b = algorithmic_bytes(conn.shape[1], m.nNode, size_local, nnz_local, m.dbc_node.size)
+    asm_b, spmv_b, cgit_b = algorithmic_bytes(npe, npe * ndof, ndim, conn.shape[1], m.nNode, size_local, nnz_local, m.dbc_node.size)
     spmv_gbs = spmv_b / spmv_avg / 1e9 if spmv_avg > 0 else 0.0
     asm_gbs = asm_b * args.steps / (t_asm if t_asm > 0 else 1) / 1e9
     cgit_gbs = cgit_b * its / t_solve / 1e9
 
     # FP64 pipe of the value pass (BASELINE.json north_star: "with the FP64 pipe reported for the element kernels"):
-    # the row-gather kernel issues 114 FP64 instructions per (row, element) incidence (no FMA by design: bit-identical to
-    # the reference's evaluation order), 4 incidences per tetrahedron; peak = SMs x 64 FP64 lanes x the SM clock under load.
+    # FP64 instructions per element of the kernel that ran (counted from the committed SASS listing, profiles/sass_*.txt;
+    # the library reports the figure of its own build), peak = SMs x 64 FP64 lanes x the SM clock under load.
     asm_fp64 = None
     asm_kernel = None
     try:
-        asm_mode = s.assembly_mode()
-        asm_kernel = {0: "assemble_kernel (row gather, binary-search slots)", 1: "assemble_sell_kernel (streamed row gather)",
-                      2: f"assemble_tiled_kernel (compute-once tiles: {asm_mode[1]} tiles, {asm_mode[2]:.2f} visits/element)"}[asm_mode[0]]
-        if asm_mode[0] != 1:
-            raise RuntimeError("FP64 instruction count below is the row-gather kernel's")
+        am = s.assembly_info()
+        asm_kernel = am["kernel"]
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
-        fp64_ops = 114.0 * 4.0 * conn.shape[1]
+        fp64_ops = am["fp64_per_visit"] * am["visits"]
         fp64_peak = sm_count * 64 * mhz * 1e6
         fp64_rate = fp64_ops * args.steps / (t_asm if t_asm > 0 else 1)
         asm_fp64 = {"ops_per_launch": fp64_ops, "achieved_gops": fp64_rate / 1e9, "peak_gops": fp64_peak / 1e9,
-                    "frac": fp64_rate / fp64_peak, "unit": "FP64 instr/s (DADD/DMUL, no FMA by design)",
+                    "frac": fp64_rate / fp64_peak, "unit": "FP64 instr/s", "visits_per_element": am["visits"] / max(conn.shape[1], 1),
+                    "fp64_instr_per_visit": am["fp64_per_visit"], "arith": am["arith"],
                     "peak_source": f"{sm_count} SMs x 64 lanes x {mhz:.0f} MHz (SM clock sampled under load)"}
     except Exception:        # reporting only: never fail the bench on it
         asm_fp64 = None
@@ -370,36 +510,45 @@ def main():
             launches_e2e += s.launch_count()
     e2e_value = N * e2e_its / e2e_t
 
-    # ---- solution sanity on every run: nodally ~exact quadratic ----
-    u = D.nodal_solution(num, xout_p)[0]
-    err = float(np.abs(u - (m.coords ** 2).sum(0)).max())
+    # ---- solution sanity on every run ----
+    u = D.nodal_solution(num, xout_p)
+    if args.workload == "c5":
+        err = float(np.abs(u[0] - (m.coords ** 2).sum(0)).max())          # nodally ~exact quadratic
+    elif args.workload == "c2":
+        from pfemfort_b200 import mesh as M
+        err = float(np.abs(u[0] - M.exact_poisson_tria(m.coords[0], m.coords[1])).max())
+    else:
+        err = None
+    max_u = float(np.sqrt((u ** 2).sum(0)).max())
 
+    cg_kernel = "cg_persistent_kernel"
+    trec, tsrc = captured_traffic(cg_kernel, args.workload, world)
+    arec, asrc = captured_traffic(asm_kernel or "assemble", args.workload, world)
     line = {
         "metric": "poisson_cg_dof_iter_per_s", "value": value, "unit": "DOF-iter/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"genTetra {args.cells}^3 x6 P1-tet Poisson on [-1,1]^3, Jacobi-CG rtol {RTOL:g}",
-                   "elements": int(m.nElem), "nodes": int(m.nNode), "dof": int(N), "nnz": nnz_total,
-                   "partition": "none" if world == 1 else args.partition, "parallelism": f"rows{world}",
-                   "exchange": {0: "none", 1: "nccl", 2: "peer-memory kernels (NVLink)"}[s.comm_mode()],
-                   "l2": "inputs larger than L2 (matrix >= 1.4 GB per pass vs 126 MB L2); no flush needed",
-                   "timing": "CUDA events on the library stream (t_assemble, t_solve), max over ranks; ms_per_step = host wall between barriers"},
-        "iterations_per_step": its_per_step, "reason": info["reason"], "max_nodal_error": err,
+        "config": {"workload": w["label"], "elements": int(m.nElem), "nodes": int(m.nNode), "dof": int(N), "nnz": nnz_total},
+        "run": {"partition": "none" if world == 1 else args.partition, "parallelism": f"rows{world}",
+                "exchange": {0: "none", 1: "nccl", 2: "peer-memory kernels (NVLink)"}[s.comm_mode()],
+                "l2": "inputs larger than L2 (matrix >= 1.4 GB per pass vs 126 MB L2); no flush needed" if nnz_local * 12 > 2.5e8
+                      else "per-rank matrix below 2x L2: the solve is L2-assisted at this size (no flush between iterations of one solve)",
+                "timing": "CUDA events on the library stream (t_assemble, t_solve), max over ranks; ms_per_step = host wall between barriers",
+                "tuning_env": {k: os.environ[k] for k in TUNING_ENV if os.environ.get(k)}},
+        "iterations_per_step": its_per_step, "reason": info["reason"], "max_nodal_error": err, "max_abs_u": max_u,
         "assembly": {"metric": "assembly_melem_per_s", "value": asm_value, "unit": "Melem/s",
                      "ms_per_pass": 1e3 * t_asm / args.steps,
-                     "roofline": {"bound": "hbm (kernel is FP64-pipe/issue bound, see DESIGN.md)", "achieved": asm_gbs, "peak": peak,
-                                  "unit": "GB/s", "frac": asm_gbs / peak,
-                                  "traffic": (3.552e9 if (world == 1 and args.cells == 200) else None), "bytes_per_launch": asm_b, "peak_source": peak_src, "scope": "rank 0 share"},
+                     "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
+                                  "traffic": arec["bytes_per_launch"] if arec else None, "traffic_source": asrc,
+                                  "bytes_per_launch": asm_b, "peak_source": peak_src, "scope": "rank 0 share"},
                      "kernel": asm_kernel, "fp64_pipe": asm_fp64},
         "cg_iteration": {"ms_per_iteration": 1e3 * t_solve / max(its, 1), "achieved_gbs": cgit_gbs, "frac": cgit_gbs / peak,
                          "bytes_per_iteration": cgit_b},
         # dominant kernel = the persistent CG kernel (one cooperative launch per solve: set-up + every iteration);
         # duration = CUDA events on the launching stream around that launch, live in the timed steps above
-        "roofline": {"bound": "hbm", "kernel": "cg_persistent_kernel", "achieved": cgit_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": cg_kernel, "achieved": cgit_gbs, "peak": peak, "unit": "GB/s",
                      "frac": cgit_gbs / peak,
-                     # dram__bytes_read+write of this kernel from the committed ncu --set full capture (profiles/r01_ncu_final_c5.txt:
-                     # 37.31 GB for set-up + 16 iterations of C5 on one GPU = 2.27 GB per iteration), scaled to this launch
-                     "traffic": (2.27e9 * its_per_step if (world == 1 and args.cells == 200) else None),
+                     "traffic": (trec["bytes_per_iteration"] * its_per_step if trec else None), "traffic_source": tsrc,
                      "bytes_per_launch": cgit_b * its_per_step,
                      "avg_launch_us": 1e6 * t_solve / args.steps, "launches_timed": args.steps,
                      "bytes_per_iteration": cgit_b, "peak_source": peak_src, "scope": "rank 0 share"},
@@ -412,28 +561,47 @@ def main():
         "gpu_launches": launches_total, "gpu_launches_e2e": launches_e2e,
         "setup_s": t_setup, "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload, and the parity record ----
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         from oracle import pyoracle as O
-        threads = O.num_threads()
+        threads = host_threads()
         rp, col, val = s.get_csr()
         rhs = s.get_rhs()
-        ne = min(args.cpu_elems, m.nElem)
+        ne = min(args.cpu_elems or m.nElem, m.nElem)
         mask = np.zeros(m.nElem, np.uint8)
         mask[:ne] = 1
         v2, r2 = np.zeros_like(val), np.zeros_like(rhs)
         t0 = time.perf_counter()
-        O.assemble(O.POISSON_TETRA, num.conn_new, m.coords, None, num.elemDof, num.solnApplied, ed, td, rp, col, elem_mask=mask,
+        O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied, ed, td, rp, col, elem_mask=mask,
                    threads=threads, val=v2, rhs=r2)
         t1 = time.perf_counter()
-        O.cg_jacobi(rp, col, val, rhs, rtol=RTOL, threads=threads, fixed_its=args.cpu_its)
+        for r_, v_ in zip(fbc_rows, fbc_vals):
+            r2[r_] += v_
+        its_cap = args.cpu_its if args.cpu_its >= 0 else w["cpu_its"]
+        _, oits, oreason, _ = O.cg_jacobi(rp, col, val, rhs, rtol=RTOL, max_it=w["max_it"], threads=threads, fixed_its=its_cap)
         t2 = time.perf_counter()
+        its_done = its_cap if its_cap else oits
         line["cpu_baseline"] = {
-            "value": N * args.cpu_its / (t2 - t1), "unit": "DOF-iter/s", "cores": threads, "kind": "port",
+            "value": N * its_done / (t2 - t1), "unit": "DOF-iter/s", "cores": threads, "kind": "port",
             "assembly_melem_per_s": ne / (t1 - t0) / 1e6,
-            "sample": f"first {ne} of {m.nElem} elements assembled ({t1 - t0:.1f} s); {args.cpu_its} CG iterations on the full system ({t2 - t1:.1f} s)",
+            "sample": f"first {ne} of {m.nElem} elements assembled ({t1 - t0:.1f} s); {its_done} CG iterations on the full system ({t2 - t1:.1f} s)"
+                      + ("" if its_cap else ", solve to tolerance"),
             "note": "CPU restatement of the PETSc/MPI path (PETSc unavailable): OpenMP oracle on the box's host cores"}
+        if not args.no_parity:
+            # the threaded oracle adds with atomics (unordered): agreement to rounding, not bit-identity, is the claim
+            par = {"oracle": f"OpenMP element loop, {threads} threads (unordered adds: agreement to rounding is the claim)",
+                   "its_gpu": int(info["its"]), "its_oracle": (int(oits) if not its_cap else None),
+                   "reason_gpu": int(info["reason"]), "reason_oracle": (int(oreason) if not its_cap else None),
+                   "tolerance": 1e-12}
+            if ne == m.nElem:
+                dv, nv = diff_stats(val, v2)
+                dr, nr = diff_stats(rhs, r2)
+                par.update({"values_max_rel": dv, "rhs_max_rel": dr, "values_differing_entries": nv, "rhs_differing_entries": nr,
+                            "within_tolerance": bool(dv <= 1e-12 and dr <= 1e-12)})
+            line["parity"] = par
     s.free()
     if rank == 0:
         print(json.dumps(line), flush=True)

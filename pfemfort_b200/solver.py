@@ -288,6 +288,15 @@ class SolverB200:
         _chk(self._lib.pfem_solver_assembly_mode(self._h, C.byref(m), C.byref(n), C.byref(v)))
         return m.value, n.value, v.value
 
+    def assembly_info(self):
+        """Kernel of the last value pass, its FP64 instructions per element visit (counted from the SASS of this
+        build, profiles/sass_*.txt), the element visits of one pass and the arithmetic mode."""
+        name = C.create_string_buffer(256)
+        fp64, visits, arith = C.c_double(), C.c_longlong(), C.c_int()
+        _chk(self._lib.pfem_solver_assembly_info(self._h, name, 256, C.byref(fp64), C.byref(visits), C.byref(arith)))
+        return dict(kernel=name.value.decode(), fp64_per_visit=fp64.value, visits=visits.value,
+                    arith={0: "no-FMA (reference evaluation order)", 1: "FMA (1e-12 contract)"}.get(arith.value, str(arith.value)))
+
     def launch_count(self, reset: bool = False) -> int:
         n = C.c_longlong()
         _chk(self._lib.pfem_solver_launch_count(self._h, C.byref(n), 1 if reset else 0))
