@@ -43,6 +43,15 @@ enum { PFEM_SOLVER_EMPTY = 1, PFEM_PATTERN_OK = 2, PFEM_INIT_OK = 3, PFEM_ASSEMB
 /* preconditioners (PCSetFromOptions, solverpetsc.F:202-210); the north-star run uses -pc_type jacobi */
 enum { PFEM_PC_NONE = 0, PFEM_PC_JACOBI = 1 };
 
+/* value-pass kernel selection (pfem_solver_set_assembly_mode; the environment variable PFEM_ASM overrides it) */
+enum { PFEM_ASM_AUTO = 0, PFEM_ASM_ROWS = 1, PFEM_ASM_FAST = 2 };
+/* FP64 instructions per element visit of the tile kernel, counted in the SASS of this build (profiles/r02_sass_value_pass.txt) */
+#define PFEM_FP64_PER_VISIT_CTILE_TET 0.0
+#define PFEM_FP64_PER_VISIT_CTILE_TRIA 0.0
+/* FP64 instructions per (row, element) incidence of the default (FMA) row-gather kernel, same source */
+#define PFEM_FP64_PER_INCIDENCE_FAST_TET 0.0
+#define PFEM_FP64_PER_INCIDENCE_FAST_TRIA 0.0
+
 /* element kinds */
 enum { PFEM_POISSON_TRIA = 0, PFEM_POISSON_TETRA = 1, PFEM_ELASTICITY_TRIA = 2, PFEM_ELASTICITY_TETRA = 3 };
 
@@ -167,10 +176,20 @@ int pfem_solver_get_info(pfem_solver_t *h, int *its, int *reason, double *rnorm,
 int pfem_solver_get_state(pfem_solver_t *h, int *state, int *row_start, int *row_end, int *size_global);
 /* exchange path in use for nranks > 1: 0 = single rank, 1 = NCCL send/recv + all-reduce, 2 = peer-memory kernels (NVLink, CUDA IPC) */
 int pfem_solver_comm_mode(pfem_solver_t *h, int *mode);
-/* kernel used by the last value pass: 0 = generic row gather (binary-search slots), 1 = streamed row gather (default),
- * 2 = tiled compute-once kernel (opt-in, PFEM_ASM=tiled, Poisson kinds); for mode 2 also the number of row tiles and the
- * mean number of times an element is computed (1.0 = every element exactly once; the row gather computes a tet 4 times) */
+/* kernel used by the last value pass: 0 = generic row gather (binary-search slots, reference arithmetic), 1 = streamed row
+ * gather with the reference-order no-FMA arithmetic (default), 2 = round-1 tiled compute-once kernel (opt-in,
+ * PFEM_ASM=tiled|tiled2), 3 = colour-scheduled tile kernel (opt-in, PFEM_ASM=ctile), 4 = streamed row gather with the FMA
+ * element operators (opt-in, PFEM_ASM=fast); for mode 2 also the number of row tiles and the mean number of times an element is computed */
 int pfem_solver_assembly_mode(pfem_solver_t *h, int *mode, int *ntiles, double *visits_per_element);
+/* Which arithmetic the value pass uses (no reference counterpart: PETSc's MatSetValues has one code path).  Both sum every
+ * matrix entry in the reference's sequential element order (tetrapoissonparallelimpl1.F:828-884), deterministically.
+ * PFEM_ASM_ROWS (= PFEM_ASM_AUTO, the default): the reference's no-FMA evaluation order of Ke/Fe -- bit-identical to a
+ * sequential np=1 CPU run.
+ * PFEM_ASM_FAST: FMA-contracted element operators (cofactor form for the Poisson kinds) -- values agree with the reference
+ * evaluation order to rounding (<= 1e-12 relative, the north-star contract), not bit for bit; 5 % faster on C5. */
+int pfem_solver_set_assembly_mode(pfem_solver_t *h, int mode);
+/* name of the kernel of the last value pass, its FP64 instructions per element visit, visits per pass, arithmetic (0 no-FMA, 1 FMA) */
+int pfem_solver_assembly_info(pfem_solver_t *h, char *kernel, int cap, double *fp64_per_visit, long long *visits, int *arith);
 /* kernel launches issued on this handle since the last call with reset != 0 */
 int pfem_solver_launch_count(pfem_solver_t *h, long long *launches, int reset);
 /* Run the CG SpMV (w = A p on an internal vector) `reps` times and report the mean device time per

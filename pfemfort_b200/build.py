@@ -23,7 +23,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
 NO_FMA = {"elements.cu", "assembly.cu", "assembly_tiled.cu"}
 # host-side set-up loops (tile construction) use OpenMP
 OPENMP = {"assembly_tiled.cu"}
-SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "cg.cu", "comm.cu", "host_driver.cu", "host_meshio.cu"]
+SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "assembly_ctile.cu", "assembly_fast.cu", "cg.cu", "comm.cu", "host_driver.cu",
+           "host_meshio.cu"]
 
 
 def _nvcc() -> str:
@@ -54,6 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     objs = []
     log = []
+    cmds = []
     for src in SOURCES:
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         cmd = [nvcc, *ARCH, *COMMON, "-c", os.path.join(CSRC, src), "-o", obj]
@@ -61,12 +63,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-fmad=false")
         if src in OPENMP:
             cmd[1:1] = ["-Xcompiler", "-fopenmp"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        cmds.append((src, cmd))
+        objs.append(obj)
+    # translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda sc: (sc[0], sc[1], subprocess.run(sc[1], capture_output=True, text=True)), cmds))
+    for src, cmd, r in results:
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             sys.stderr.write(log[-1])
             raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
     cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xlinker", "--exclude-libs,ALL", "-ldl", "-Xcompiler", "-fopenmp",
            "-L/usr/local/cuda/targets/x86_64-linux/lib", "-lmetis_static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -270,6 +270,18 @@ int pfem_solver_set_applied(pfem_solver_t *h, const double *solnApplied, int n)
     if (!solnApplied || n != h->nNode * h->ndof) { set_error("pfem_solver_set_applied: expected %d values", h->nNode * h->ndof); return PFEM_ERR_ARG; }
     PFEM_CUDA(cudaMemcpyAsync(h->applied.p, solnApplied, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     PFEM_CUDA(cudaStreamSynchronize(h->stream));
+    h->ct_ready = false; h->ct_tried = false;      // the tile kernel's node tables carry the applied values
+    return PFEM_OK;
+}
+
+int pfem_solver_set_assembly_mode(pfem_solver_t *h, int mode)
+{
+    PFEM_TRY(need_handle(h, "pfem_solver_set_assembly_mode"));
+    if (mode != PFEM_ASM_AUTO && mode != PFEM_ASM_ROWS && mode != PFEM_ASM_FAST) {
+        set_error("pfem_solver_set_assembly_mode: mode %d (0 auto | 1 rows | 2 fast)", mode);
+        return PFEM_ERR_ARG;
+    }
+    h->asm_mode_req = mode;
     return PFEM_OK;
 }
 
@@ -445,6 +457,45 @@ int pfem_solver_assembly_mode(pfem_solver_t *h, int *mode, int *ntiles, double *
     if (ntiles) *ntiles = h->last_asm_mode == 2 ? h->ntiles : 0;
     if (visits_per_element)
         *visits_per_element = (h->last_asm_mode == 2 && h->tile_elems_touched) ? (double)h->tile_elem_visits / (double)h->tile_elems_touched : 0.0;
+    return PFEM_OK;
+}
+
+int pfem_solver_assembly_info(pfem_solver_t *h, char *kernel, int cap, double *fp64_per_visit, long long *visits, int *arith)
+{
+    if (!h) { set_error("NULL handle"); return PFEM_ERR_ARG; }
+    // FP64 instructions (DADD/DMUL/DFMA + the reciprocal sequence) per element visit, counted in the SASS of this build
+    // (tools/sass_count.py -> profiles/r02_sass_value_pass.txt); rows kernels: per (row, element) incidence
+    char buf[256];
+    double f = 0.0;
+    long long v = 0;
+    int ar = 0;
+    switch (h->last_asm_mode) {
+    case 3:
+        snprintf(buf, sizeof buf, "assemble_ctile_kernel (colour-scheduled tiles: %d tiles of <= %d rows, %d threads, %.3f visits/element, <= %d rounds)",
+                 h->ct_ntiles, h->ct_TR, h->ct_threads, h->nElem ? (double)h->ct_visits / h->nElem : 0.0, h->ct_max_rounds);
+        f = h->npe == 4 ? PFEM_FP64_PER_VISIT_CTILE_TET : PFEM_FP64_PER_VISIT_CTILE_TRIA; v = h->ct_visits; ar = 1;
+        break;
+    case 4:
+        snprintf(buf, sizeof buf, "assemble_sell_kernel<FastOp> (streamed row gather, sequential order, FMA cofactor arithmetic)");
+        f = h->kind == PFEM_POISSON_TETRA ? PFEM_FP64_PER_INCIDENCE_FAST_TET : (h->kind == PFEM_POISSON_TRIA ? PFEM_FP64_PER_INCIDENCE_FAST_TRIA : 0.0);
+        v = h->ninc; ar = 1;
+        break;
+    case 2:
+        snprintf(buf, sizeof buf, "assemble_tiled_kernel (round-1 compute-once tiles: %d tiles)", h->ntiles);
+        f = 177.0; v = h->tile_elem_visits; ar = 0;
+        break;
+    case 1:
+        snprintf(buf, sizeof buf, "assemble_sell_kernel (streamed row gather, sequential order)");
+        f = h->kind == PFEM_POISSON_TETRA ? 114.0 : 0.0; v = h->ninc; ar = 0;
+        break;
+    default:
+        snprintf(buf, sizeof buf, "assemble_kernel (row gather, binary-search slots)");
+        f = 0.0; v = h->ninc; ar = 0;
+    }
+    if (kernel && cap > 0) { strncpy(kernel, buf, (size_t)cap - 1); kernel[cap - 1] = 0; }
+    if (fp64_per_visit) *fp64_per_visit = f;
+    if (visits) *visits = v;
+    if (arith) *arith = ar;
     return PFEM_OK;
 }
 

@@ -155,9 +155,52 @@ int plan_assembly(pfem_solver *h)
     return PFEM_ERR_SIZE;
 }
 
+// which kernel runs the pass: PFEM_ASM (rows | fast | ctile | tiled | tiled2) overrides the handle's request
+// (pfem_solver_set_assembly_mode).  Default = "rows": the streamed row-gather kernel with the reference-order no-FMA element
+// operators (sequential summation order: bit-identical to the sequential CPU evaluation); "fast" = the same kernel with the
+// FMA cofactor-form operators (1e-12 contract; measured 5 % faster on C5: the kernel is issue-bound on its non-FP64
+// instructions, not on the FP64 pipe); "ctile" = the colour-scheduled tile kernel (compute-once, TMA-staged; measured slower
+// than the row gather on B200: shared-memory read-modify-write traffic and barriers, profiles/r02_value_pass.md).
+int dispatch_rows_fast(pfem_solver *h, const AsmArgs &args);     // assembly_fast.cu
+
+static int pick_mode(pfem_solver *h, int &mode)
+{
+    const char *env = getenv("PFEM_ASM");
+    int want = h->asm_mode_req == PFEM_ASM_FAST ? 0 : 1;            // 0 fast, 1 rows (default), 2 tiled, 3 tiled2, 4 ctile
+    if (env) {
+        if (!strcmp(env, "rows")) want = 1;
+        else if (!strcmp(env, "tiled")) want = 2;
+        else if (!strcmp(env, "tiled2")) want = 3;
+        else if (!strcmp(env, "ctile")) want = 4;
+        else if (!strcmp(env, "fast")) want = 0;
+        else if (!strcmp(env, "auto") || !env[0]) want = 1;
+        else { set_error("PFEM_ASM=%s: expected fast | rows | ctile | tiled | tiled2 | auto", env); return PFEM_ERR_ARG; }
+    }
+    if (want == 4) {
+        if (h->ndof == 1 && !h->ct_ready && !h->ct_tried) { h->ct_tried = true; PFEM_TRY(build_ctiles(h)); }
+        if (h->ct_ready) { mode = 3; return PFEM_OK; }
+        set_error("PFEM_ASM=ctile: the tile kernel does not apply to this pattern (kind %d)", h->kind);
+        return PFEM_ERR_ARG;
+    }
+    if (!h->rows_ready) {
+        PFEM_TRY(build_asm_streams(h));
+        h->asm_rows_per_cta = 0;
+        h->rows_ready = true;
+    }
+    if ((want == 2 || want == 3) && h->ndof == 1) {                // round-1 opt-in tiles (host-built from the row streams)
+        const int tile_mode = want - 1;
+        if (!h->tiles_ready || h->tile_mode != tile_mode) PFEM_TRY(build_tiles_device(h, tile_mode));
+        if (h->asm_tiled) { mode = 2; return PFEM_OK; }
+    }
+    if (h->asm_rows_per_cta == 0) PFEM_TRY(plan_assembly(h));
+    mode = h->asm_sell ? (want == 0 ? 4 : 1) : 0;
+    return PFEM_OK;
+}
+
 int assemble_values(pfem_solver *h, const double *elemData, const double *timeData, int *n_neg)
 {
-    if (h->asm_rows_per_cta == 0) PFEM_TRY(plan_assembly(h));
+    int mode = 0;
+    PFEM_TRY(pick_mode(h, mode));
     DevBuf<double> dED, dTD;
     PFEM_TRY(dED.alloc(8));
     PFEM_TRY(dTD.alloc(8));
@@ -179,15 +222,12 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     a.max_seg_nnz = h->asm_max_seg;
     a.ainc_off = h->ainc_off.p; a.ainc = h->ainc.p; a.conn4 = h->conn4.p; a.neg_flag = h->neg_count.p;
     a.unit = (td[1] == 1.0 && ed[0] == 1.0 && ed[1] == 1.0 && (h->kind == PFEM_POISSON_TRIA || ed[2] == 1.0)) ? 1 : 0;
-    // opt-in: the tiled (compute-once) kernel for the one-dof-per-node kinds; tiles are built once per pattern
-    const char *mode = getenv("PFEM_ASM");
-    const int tile_mode = !mode ? 0 : !strcmp(mode, "tiled") ? 1 : !strcmp(mode, "tiled2") ? 2 : 0;
-    const bool want_tiled = tile_mode != 0 && h->ndof == 1;
-    if (want_tiled && (!h->tiles_ready || h->tile_mode != tile_mode)) PFEM_TRY(build_tiles_device(h, tile_mode));
     PFEM_CUDA(cudaEventRecord(h->ev0, s));
     int st = PFEM_OK;
-    h->last_asm_mode = (want_tiled && h->asm_tiled) ? 2 : (h->asm_sell ? 1 : 0);
-    if (want_tiled && h->asm_tiled) st = assemble_values_tiled(h, dED.p, dTD.p, a.unit != 0);
+    h->last_asm_mode = mode;
+    if (mode == 3) st = assemble_values_ctile(h, dED.p, dTD.p);
+    else if (mode == 4) st = dispatch_rows_fast(h, a);
+    else if (mode == 2) st = assemble_values_tiled(h, dED.p, dTD.p, a.unit != 0);
     else switch (h->kind) {
     case PFEM_POISSON_TRIA: st = dispatch_rows<POISSON_TRIA>(h, a); break;
     case PFEM_POISSON_TETRA: st = dispatch_rows<POISSON_TETRA>(h, a); break;
@@ -200,7 +240,7 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
     int neg = 0;
     PFEM_CUDA(cudaMemcpyAsync(&neg, h->neg_count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PFEM_CUDA(cudaStreamSynchronize(s));
-    if (neg && h->asm_sell) {      // the streamed kernel only raises a flag: count the offending elements now
+    if (neg && mode != 0) {        // the streamed / tile kernels only raise a flag: count the offending elements now
         PFEM_CUDA(cudaMemsetAsync(h->neg_count.p, 0, sizeof(int), s));
         const int G = h->sm_count * 8;
         switch (h->kind) {

@@ -47,7 +47,8 @@ struct CtileArgs {
     const double *elemData, *timeData;
     int *neg_flag;
     int load_val, load_rhs;
-    int node_cap;              // shared-memory carve-up: nodes (double4), then accumulators, then RHS
+    int node_cap;              // shared-memory carve-up: nodes (double4), row descriptors (int4), accumulators, RHS, sinks
+    int row_cap;
     int acc_cap;
 };
 
@@ -94,7 +95,7 @@ template <int KIND> struct TileElem;
 template <> struct TileElem<POISSON_TETRA> {
     static constexpr int NPE = 4, NK = 10;
     double K[NK], F0, Jac;
-    __device__ __forceinline__ static int idx(int i, int j) { return i <= j ? (i * (7 - i)) / 2 + (j - i) : (j * (7 - j)) / 2 + (i - j); }
+    __device__ __forceinline__ static int idx(int i, int j) { return i <= j ? (i * (9 - i)) / 2 + (j - i) : (j * (9 - j)) / 2 + (i - j); }
     __device__ __forceinline__ void compute(const double4 (&P)[4], const Params<POISSON_TETRA> &p, bool unit)
     {
         // rows of B: nodes 0, 1, 3 relative to node 2 (basisfuncs.F:493-509)
@@ -129,7 +130,7 @@ template <> struct TileElem<POISSON_TETRA> {
 template <> struct TileElem<POISSON_TRIA> {
     static constexpr int NPE = 3, NK = 6;
     double K[NK], F0, Jac;
-    __device__ __forceinline__ static int idx(int i, int j) { return i <= j ? (i * (5 - i)) / 2 + (j - i) : (j * (5 - j)) / 2 + (i - j); }
+    __device__ __forceinline__ static int idx(int i, int j) { return i <= j ? (i * (7 - i)) / 2 + (j - i) : (j * (7 - j)) / 2 + (i - j); }
     __device__ __forceinline__ void compute(const double4 (&P)[4], const Params<POISSON_TRIA> &p, bool unit)
     {
         const double ax = P[1].x - P[0].x, ay = P[1].y - P[0].y;      // basisfuncs.F:208-217
@@ -157,15 +158,21 @@ template <> struct TileElem<POISSON_TRIA> {
     }
 };
 
-template <int KIND, int B>
+// SUBSYNC = true : the rounds were built with the per-position rule (no two visits of a round share an owned row at the
+//                   same local position k): column k of every visit is committed, then __syncthreads, then k + 1.
+// SUBSYNC = false: the rounds were built with the full rule (no two visits of a round share an owned row at all): every
+//                   visit commits all its columns at once, one __syncthreads per chunk.
+template <int KIND, int B, bool SUBSYNC>
 __global__ void __launch_bounds__(B, 1) assemble_ctile_kernel(const CtileArgs a)
 {
     using E = TileElem<KIND>;
     constexpr int NPE = E::NPE;
     extern __shared__ __align__(128) unsigned char ct_smem[];
     double4 *snode = reinterpret_cast<double4 *>(ct_smem);
-    double *acc = reinterpret_cast<double *>(snode + a.node_cap);
+    int4 *strow = reinterpret_cast<int4 *>(snode + a.node_cap);
+    double *acc = reinterpret_cast<double *>(strow + a.row_cap);
     double *frhs = acc + a.acc_cap;
+    double *sink = frhs + a.row_cap + threadIdx.x;          // Dirichlet columns are added here (never read back)
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ int s_roff[CT_MAX_ROUNDS + 2];
 
@@ -173,12 +180,13 @@ __global__ void __launch_bounds__(B, 1) assemble_ctile_kernel(const CtileArgs a)
     Params<KIND> prm;
     prm.init(a.elemData, a.timeData);
     bool unit = prm.af == 1.0 && prm.kx == 1.0 && prm.ky == 1.0;
-    if (KIND == POISSON_TETRA) unit = unit && reinterpret_cast<const Params<POISSON_TETRA> &>(prm).kz == 1.0;
+    if constexpr (KIND == POISSON_TETRA) unit = unit && prm.kz == 1.0;
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    *sink = 0.0;
     __syncthreads();
     unsigned parity = 0;
 
@@ -186,31 +194,33 @@ __global__ void __launch_bounds__(B, 1) assemble_ctile_kernel(const CtileArgs a)
         const int *td = a.tdesc + (size_t)tile * CT_DESC;
         const int row0 = td[CT_ROW0], nrows = td[CT_NROWS], node0 = td[CT_NODE0], nnodes = td[CT_NNODES];
         const int round0 = td[CT_ROUND0], nrounds = td[CT_NROUNDS], stride = td[CT_STRIDE];
-        // ---- stage the tile's node table (bulk async copy) while the accumulators are initialised ----
+        // ---- stage the tile's node table and row descriptors (bulk async copies) while the accumulators are zeroed ----
         if (tid == 0) {
-            fence_proxy_async();                 // the previous tile's generic-proxy reads of snode precede this async write
-            const unsigned bytes = (unsigned)nnodes * 32u;
-            mbar_expect_tx(&mbar, bytes);
-            bulk_g2s(snode, a.tnode + node0, bytes, &mbar);
+            fence_proxy_async();                 // the previous tile's generic-proxy reads of the staged tables precede these writes
+            const unsigned nb = (unsigned)nnodes * 32u, rb = (unsigned)nrows * 16u;
+            mbar_expect_tx(&mbar, nb + rb);
+            bulk_g2s(snode, a.tnode + node0, nb, &mbar);
+            bulk_g2s(strow, a.trow + row0, rb, &mbar);
             const int nt = tile + gridDim.x;
             if (nt < a.ntiles) {
                 const int *nd = a.tdesc + (size_t)nt * CT_DESC;
                 bulk_prefetch_l2(a.tnode + nd[CT_NODE0], (unsigned)nd[CT_NNODES] * 32u);
+                bulk_prefetch_l2(a.trow + nd[CT_ROW0], (unsigned)nd[CT_NROWS] * 16u);
             }
         }
         for (int q = tid; q <= nrounds; q += B) s_roff[q] = a.round_off[round0 + q];
         const int nacc = nrows * stride;
-        if (!a.load_val) {
-            for (int q = tid; q < nacc; q += B) acc[q] = 0.0;
-        } else {
-            for (int i = tid >> 4; i < nrows; i += B >> 4) {
-                const int4 tr = __ldg(a.trow + row0 + i);
-                for (int j = tid & 15; j < tr.z; j += 16) acc[i * stride + j] = a.val[tr.y + j];
-            }
-        }
-        for (int i = tid; i < nrows; i += B) frhs[i] = a.load_rhs ? a.rhs[__ldg(a.trow + row0 + i).x] : 0.0;
+        if (!a.load_val) for (int q = tid; q < nacc; q += B) acc[q] = 0.0;
+        if (!a.load_rhs) for (int i = tid; i < nrows; i += B) frhs[i] = 0.0;
         mbar_wait(&mbar, parity);
         parity ^= 1u;
+        if (a.load_val | a.load_rhs) {           // ADD on top of the current values (no setZero since the last pass)
+            for (int i = tid >> 4; i < nrows; i += B >> 4) {
+                const int4 tr = strow[i];
+                if (a.load_val) for (int j = tid & 15; j < tr.z; j += 16) acc[i * stride + j] = a.val[tr.y + j];
+                if (a.load_rhs && (tid & 15) == 0) frhs[i] = a.rhs[tr.x];
+            }
+        }
         __syncthreads();
 
         // ---- rounds ----
@@ -244,26 +254,40 @@ __global__ void __launch_bounds__(B, 1) assemble_ctile_kernel(const CtileArgs a)
                 if (active && w[k] != ~0u) {
                     const unsigned rl = (k < 2 ? (vn.x >> (16 * k)) : (vn.y >> (16 * (k - 2)))) & 0xFFFFu;
                     double *ra = acc + rl * stride;
-                    double f = el.Fk(k);
-                    // MatSetValues(ADD): entry (row k, col j) += Klocal(j, k) (= Klocal(k, j) in this symmetric form);
-                    // a Dirichlet column (slot byte 0xFF) goes to the lifting instead: F_k -= Klocal(k, j) * g_j
+                    // MatSetValues(ADD): entry (row k, col j) += Klocal(j, k) (= Klocal(k, j) in this symmetric form).
+                    // The free columns of an element are distinct entries of the row: all loads first, then all stores.
+                    // A Dirichlet column (slot byte 0xFF) lands in the sink and goes to the lifting instead.
+                    double *dst[NPE];
+                    double cur[NPE];
 #pragma unroll
                     for (int j = 0; j < NPE; j++) {
                         const unsigned sl = (w[k] >> (8 * j)) & 255u;
-                        const double kv = el.K[E::idx(k, j)];
-                        if (sl != 255u) ra[sl] += kv;
-                        else f = fma(-kv, gval[j], f);
+                        dst[j] = sl == 255u ? sink : ra + sl;
                     }
-                    frhs[rl] += f;                                  // VecSetValues(ADD)
+#pragma unroll
+                    for (int j = 0; j < NPE; j++) cur[j] = *dst[j];
+                    const double fr = frhs[rl];
+                    double f = el.Fk(k);
+                    const unsigned nw = ~w[k];                     // a 0xFF slot byte becomes a zero byte
+                    if (((nw - 0x01010101u) & ~nw & 0x80808080u) != 0u) {
+                        // lifting: F_k -= Klocal(k, j) * g_j over the Dirichlet local nodes j (tetrapoissonparallelimpl1.F:856-872)
+#pragma unroll
+                        for (int j = 0; j < NPE; j++)
+                            if (((w[k] >> (8 * j)) & 255u) == 255u) f = fma(-el.K[E::idx(k, j)], gval[j], f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NPE; j++) *dst[j] = cur[j] + el.K[E::idx(k, j)];
+                    frhs[rl] = fr + f;                              // VecSetValues(ADD)
                 }
-                __syncthreads();
+                if (SUBSYNC) __syncthreads();
             }
+            if (!SUBSYNC) __syncthreads();
             vn = vn2; vs = vs2; base = nbase; r = nr; vend = nend;
         }
 
         // ---- write-out: accumulators -> CSR values / RHS, half a warp per row ----
         for (int i = tid >> 4; i < nrows; i += B >> 4) {
-            const int4 tr = __ldg(a.trow + row0 + i);
+            const int4 tr = strow[i];
             for (int j = tid & 15; j < tr.z; j += 16) a.val[tr.y + j] = acc[i * stride + j];
             if ((tid & 15) == 0) a.rhs[tr.x] = frhs[i];
         }

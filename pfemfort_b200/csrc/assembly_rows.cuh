@@ -158,7 +158,9 @@ __device__ __forceinline__ void ld_xyz(const double *p, double &x, double &y, do
 // The loop is software-pipelined: incidence entries three iterations ahead, node ids two ahead, and the next
 // iteration's coordinates already in flight into registers while the current element is computed.
 // UNIT: kx = ky = kz = af = 1.0 exactly (the drivers' constants): multiplications by 1.0 are skipped (bit-identical).
-template <int KIND, int R, bool UNIT>
+// OP: the element operator -- ElemOp<KIND> (reference evaluation order; its translation unit is built with -fmad=false) or
+// FastOp<KIND> (elements_fast.cuh: FMA-contracted cofactor form; 1e-12 contract).
+template <int KIND, int R, bool UNIT, class OP = ElemOp<KIND>>
 __global__ void __launch_bounds__(R) assemble_sell_kernel(const AsmArgs a)
 {
     using T = ElemTraits<KIND>;
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(R) assemble_sell_kernel(const AsmArgs a)
             if (cur.code < 0) continue;                    // slice padding
             const int k = cur.code % NSIZE;
             const int nodes[4] = {cn.x, cn.y, cn.z, cn.w};
-            ElemOp<KIND> op;
+            OP op;
             op.load_geom(x, y, z);
             if (op.g.Jac < 0.0) { atomicOr(a.neg_flag, 1); continue; }   // the reference STOPs here
             op.set_dvol(prm);

@@ -156,6 +156,15 @@ struct pfem_solver {
     pfem::DevBuf<unsigned char> t_cnt;
     pfem::DevBuf<long long> t_slice_off;
     pfem::DevBuf<char> scratch[8];         // persistent set-up scratch (sort buffers, upload staging), re-used across calls
+    // colour-scheduled tile value pass (default for one dof per node): assembly_ctile.cu / .cuh
+    bool ct_ready = false, ct_tried = false, rows_ready = false, ct_full = true;
+    int asm_mode_req = 0;                  // 0 auto (tile kernel when it applies), 1 row kernels (bit-identical to the sequential order)
+    int ct_ntiles = 0, ct_TR = 0, ct_stride = 0, ct_node_cap = 0, ct_max_rounds = 0, ct_threads = 0;
+    long long ct_visits = 0;
+    size_t ct_smem = 0;
+    pfem::DevBuf<int> ct_tdesc, ct_trow, ct_round_off;
+    pfem::DevBuf<unsigned int> ct_vnode, ct_vslot;
+    pfem::DevBuf<double> ct_tnode;
 
     // solver
     pfem::SellMatrix A;                    // diagonal block
@@ -212,6 +221,11 @@ int plan_assembly(pfem_solver *h);
 int assemble_values(pfem_solver *h, const double *elemData, const double *timeData, int *n_neg);
 int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const double *vals, bool transposed,
                 const double *F);
+// assembly_ctile.cu
+int build_ctiles(pfem_solver *h);
+int assemble_values_ctile(pfem_solver *h, const double *dElemData, const double *dTimeData);
+// pattern.cu: streams of the row kernels (built on first use)
+int build_asm_streams(pfem_solver *h);
 // assembly_tiled.cu
 int build_tiles_device(pfem_solver *h, int mode);
 int assemble_values_tiled(pfem_solver *h, const double *dElemData, const double *dTimeData, bool unit);

@@ -289,8 +289,9 @@ __global__ void fill_asm_inc_kernel(int nloc, int nrows_padded, int nsize, int n
     }
 }
 
-static int build_asm_streams(pfem_solver *h)
+int build_asm_streams(pfem_solver *h)
 {
+    StageTimer tm("value pass: row-kernel streams");
     cudaStream_t s = h->stream;
     const int G = h->sm_count * 8, nloc = h->size_local;
     const int nslices = (nloc + 31) / 32;
@@ -471,17 +472,15 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof, cons
     h->values_zero = true;
     h->rhs_zero = true;
     PFEM_TRY(h->neg_count.alloc(1));
-    {
-        StageTimer tm("pattern: value-pass streams");
-        PFEM_TRY(build_asm_streams(h));
-    }
+    // the value-pass streams (row kernels: build_asm_streams + plan_assembly; tile kernel: build_ctiles) are built on
+    // first use by assemble_values, for the kernel that actually runs
+    h->asm_sell = false;
+    h->rows_ready = false;
     h->asm_rows_per_cta = 0;
     h->tiles_ready = false;            // tiles of the previous pattern (if any) are stale
     h->asm_tiled = false;
-    {
-        StageTimer tm("pattern: plan assembly");
-        PFEM_TRY(plan_assembly(h));
-    }
+    h->ct_ready = false;
+    h->ct_tried = false;
     return PFEM_OK;
 }
 

@@ -130,6 +130,9 @@ def element_ke(kind, x, y, z, elemData, timeData, valC=None):
     return K.reshape(ns, ns).T.copy(), F
 
 
+ASM_AUTO, ASM_ROWS, ASM_FAST = 0, 1, 2
+
+
 class SolverB200:
     """Drop-in for ``TYPE(PetscSolver)``: one instance per rank / GPU."""
 
@@ -287,6 +290,11 @@ class SolverB200:
         m, n, v = C.c_int(), C.c_int(), C.c_double()
         _chk(self._lib.pfem_solver_assembly_mode(self._h, C.byref(m), C.byref(n), C.byref(v)))
         return m.value, n.value, v.value
+
+    def set_assembly_mode(self, mode: int):
+        """ASM_AUTO / ASM_ROWS (default: reference-order no-FMA arithmetic, bit-identical to the sequential evaluation) or
+        ASM_FAST (FMA cofactor-form arithmetic, 1e-12 contract)."""
+        _chk(self._lib.pfem_solver_set_assembly_mode(self._h, int(mode)))
 
     def assembly_info(self):
         """Kernel of the last value pass, its FP64 instructions per element visit (counted from the SASS of this

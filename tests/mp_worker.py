@@ -89,6 +89,7 @@ def main():
         rhs = s.get_rhs()
         x = s.get_solution()
         result["comm_mode"] = s.comm_mode()
+        result["assembly_mode"] = s.assembly_mode()[0]
         parts = [None] * world
         dist.all_gather_object(parts, (rp, col, val, rhs, info["its"], info["reason"]))
         if rank == 0:
@@ -103,6 +104,11 @@ def main():
                                                    np.array_equal(np.concatenate([p[1] for p in parts]), gcol))
             result["values_bit_identical"] = bool(np.array_equal(np.concatenate([p[2] for p in parts]), gval))
             result["rhs_bit_identical"] = bool(np.array_equal(np.concatenate([p[3] for p in parts]), grhs))
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from properties import values_within, vector_within
+            result["values_within_1e-12"] = bool(result["pattern_bit_identical"] and
+                                                 values_within(grp, np.concatenate([p[2] for p in parts]), gval))
+            result["rhs_within_1e-12"] = bool(vector_within(np.concatenate([p[3] for p in parts]), grhs))
             result["its"] = [int(p[4]) for p in parts]
             result["reason"] = [int(p[5]) for p in parts]
             result["oracle_its"] = int(oits)

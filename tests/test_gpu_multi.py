@@ -17,11 +17,14 @@ def _ngpu():
 
 @pytest.mark.parametrize("mesh,nproc,port", [("tet10", 2, 29621), ("beam3Dtet6366", 2, 29622), ("cookmembranetria32", 2, 29623),
                                              ("gen_tet24", 2, 29624), ("gen_tet24", 4, 29625), ("gen_tet24", 8, 29626)])
-@pytest.mark.parametrize("comm", ["p2p", "nccl"])
-def test_multi_gpu_matches_oracle(gpu, tmp_path, mesh, nproc, port, comm):
+@pytest.mark.parametrize("comm,asm", [("p2p", "rows"), ("p2p", "fast"), ("nccl", "rows")])
+def test_multi_gpu_matches_oracle(gpu, tmp_path, mesh, nproc, port, comm, asm):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     os.environ["PFEM_COMM"] = comm          # p2p: peer-memory kernels over NVLink (default); nccl: the NCCL path
+    os.environ.pop("PFEM_ASM", None)
+    if asm == "fast":
+        os.environ["PFEM_ASM"] = "fast"     # FMA element operators: 1e-12 contract instead of bit-identity
     out = os.path.join(str(tmp_path), "result.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), "--mode", "gpu", "--mesh", mesh, "--out", out]
@@ -29,7 +32,12 @@ def test_multi_gpu_matches_oracle(gpu, tmp_path, mesh, nproc, port, comm):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.load(open(out))
     assert res["comm_mode"] == (2 if comm == "p2p" else 1)
-    assert res["pattern_bit_identical"] and res["values_bit_identical"] and res["rhs_bit_identical"]
+    os.environ.pop("PFEM_ASM", None)
+    assert res["pattern_bit_identical"] and res["values_within_1e-12"] and res["rhs_within_1e-12"]
+    if asm == "rows":
+        assert res["assembly_mode"] in (0, 1) and res["values_bit_identical"] and res["rhs_bit_identical"]
+    else:
+        assert res["assembly_mode"] == 4
     assert all(x == res["oracle_reason"] == 2 for x in res["reason"])
     assert len(set(res["its"])) == 1
     assert abs(res["its"][0] - res["oracle_its"]) <= max(1, 0.02 * res["oracle_its"])

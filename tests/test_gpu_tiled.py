@@ -65,8 +65,8 @@ def test_tiled_value_pass_bit_identical(gpu, input_dir, tiled_env, name, threads
     assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
     assert np.array_equal(val, oval), "tiled values not bit-identical to the no-FMA oracle"
     assert np.array_equal(rhs, orhs)
-    # and to the default kernel
-    del tiled_env["PFEM_ASM"]
+    # and to the row-gather kernel
+    tiled_env["PFEM_ASM"] = "rows"
     _, _, dval, drhs, dmode = _assemble(m, kind, num)
     assert dmode[0] == 1 and np.array_equal(val, dval) and np.array_equal(rhs, drhs)
 

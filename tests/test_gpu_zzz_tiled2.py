@@ -3,9 +3,7 @@ is stored at its final position in a run-ordered shared-memory buffer and each r
 ("deterministic segmented reduction by slot").  Bit-identical to the oracle in the CPU emulation
 (tests/test_tiled_emu.py, ids "scatter").
 
-This kernel was written after the round-1 GPU budget was spent: it has not run on hardware yet.  The tests are therefore
-marked xfail(strict=False) and sorted last: a pass shows up as XPASS, a failure cannot hide another test's result.
-Remove the marker after the first green run on a B200.
+First run on a B200 by the round-1 driver (10 XPASS); the xfail marker was removed in round 2.
 """
 import os
 
@@ -15,8 +13,7 @@ import pytest
 from oracle import pyoracle as O
 from pfemfort_b200 import driver as D, mesh as M, solver as S
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="assemble_tiled2_kernel: emulation-verified, not yet run on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()
@@ -78,6 +75,6 @@ def test_scatter_value_pass_full_size_c5_equals_default(gpu, env):
     num = D.number(m, S.POISSON_TETRA)
     _, _, v2, r2, mode = _assemble(m, S.POISSON_TETRA, num)
     assert mode[0] == 2
-    del env["PFEM_ASM"]
+    env["PFEM_ASM"] = "rows"
     _, _, v1, r1, mode1 = _assemble(m, S.POISSON_TETRA, num)
     assert mode1[0] == 1 and np.array_equal(v1, v2) and np.array_equal(r1, r2)
