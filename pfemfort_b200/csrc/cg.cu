@@ -768,6 +768,7 @@ struct PcgArgs {
     double *bcast;                         // 4 PcgSlot {value, epoch}: [0..2] reduction results, [3] ok flag / release
     unsigned long long *arrive;            // monotonically increasing CTA arrival counter of the barriers
     unsigned int *push_ticket;             // monotonically increasing CTA arrival counter of the halo pushes
+    double *a2a;                           // all-to-all barrier: PcgSlot [2 parities][3 values][pstride] (pcg_sync_a2a)
 };
 
 __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
@@ -868,17 +869,141 @@ __device__ __forceinline__ bool pcg_sync(const PcgArgs &a, double (&v)[NV > 0 ? 
     return okall;
 }
 
+// All-to-all variant of the barrier (SYNC = 1): no arrival counter, no "last CTA", no second hop.  Every CTA publishes its NV
+// block sums as tag-validated 16-byte slots {value, seq:epoch} (one release fence by thread 0 orders the CTA's writes of
+// the phase before them) and then EVERY CTA polls all the slots itself, one slot per thread, and forms the grid sum in
+// the same fixed order => identical in all CTAs and run-to-run deterministic.  Critical path per phase: one fence, one
+// store, one poll round trip and three CTA barriers, against ~8 dependent L2 round trips of the counter scheme.
+// Slots are double-buffered by epoch parity: CTA i rewrites slot[parity] two barriers later, i.e. only after every CTA
+// has published for the barrier in between, which it does after it finished reading this one.
+// For nranks > 1 CTA 0 forwards the local sums into the peers' mailboxes and the first warp of EVERY CTA polls the local
+// mailbox: the cross-rank sum needs no local re-broadcast either.
+// The sums are valid in thread 0 only (the only consumer: the scalar step); v[] holds per-thread partial sums on entry.
+template <int NV>
+__device__ __forceinline__ bool pcg_sync_a2a(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
+                                             unsigned long long &epoch, unsigned long long seq, double *sh2)
+{
+    constexpr int NS = NV > 0 ? NV : 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    epoch++;
+    const unsigned long long tag = (seq << 32) | (epoch & 0xffffffffULL);
+    PcgSlot *slots = reinterpret_cast<PcgSlot *>(a.a2a) + (size_t)(epoch & 1ULL) * 3 * a.pstride;
+    double *sh = sh2 + (epoch & 1ULL) * 192;         // [2 stages][3 values][32 warps], double-buffered by parity
+    if (NV > 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) { const double t = warp_sum(v[i]); if (lane == 0) sh[i * 32 + wid] = t; }
+    }
+    __syncthreads();                                 // the CTA's writes of this phase precede thread 0's release fence
+    if (wid == 0) {
+        double t[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            t[i] = 0.0;
+            if (NV > 0) { t[i] = lane < (int)(blockDim.x >> 5) ? sh[i * 32 + lane] : 0.0; t[i] = warp_sum(t[i]); }
+        }
+        if (lane == 0) {
+            __threadfence();
+#pragma unroll
+            for (int i = 0; i < NS; i++) st_slot_gpu(slots + (size_t)i * a.pstride + blockIdx.x, t[i], tag);
+        }
+    }
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) acc[i] = 0.0;
+    bool ok = true;
+    if ((int)threadIdx.x < (int)gridDim.x) {
+        const long long c0 = clock64();
+        for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+            double val[NS];
+            unsigned long long tg[NS];
+#pragma unroll
+            for (int i = 0; i < NS; i++) ld_slot_gpu(slots + (size_t)i * a.pstride + c, val[i], tg[i]);
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                while (ok && tg[i] != tag) {
+                    if (clock64() - c0 > 40000000000LL) ok = false;           // ~20 s: never hang the GPU
+                    ld_slot_gpu(slots + (size_t)i * a.pstride + c, val[i], tg[i]);
+                }
+                acc[i] += val[i];
+            }
+        }
+        __threadfence();                             // acquire: the other CTAs' writes of this phase are visible from here on
+    }
+    double *shb = sh + 96;
+    if (NV > 0 && wid < (int)((gridDim.x + 31) >> 5)) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) { const double t = warp_sum(acc[i]); if (lane == 0) shb[i * 32 + wid] = t; }
+    }
+    ok = __syncthreads_and(ok ? 1 : 0) != 0;
+    if (NV > 0 && wid == 0) {
+        int nw = (int)((gridDim.x + 31) >> 5);
+        if (nw > (int)(blockDim.x >> 5)) nw = (int)(blockDim.x >> 5);
+        double r[NS];
+#pragma unroll
+        for (int i = 0; i < NV; i++) { r[i] = lane < nw ? shb[i * 32 + lane] : 0.0; r[i] = warp_sum(r[i]); }
+        if (a.multi) {
+            // cross-rank sum: CTA 0 forwards, everybody polls the local mailbox, rank-order sum (bit-identical everywhere)
+            const P2pCtx *c = a.ctx;
+            const int P = c->nranks, me = c->rank;
+            if (lane < P) {
+                if (blockIdx.x == 0) {
+                    P2pMail *dst = c->mail[lane];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) st_slot_sys(&dst->red[phase][me][i], r[i], ptag);
+                }
+                const P2pMail *mine = c->mail[me];
+                const long long t0 = clock64();
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    double val;
+                    unsigned long long tg;
+                    ld_slot_sys(&mine->red[phase][lane][i], val, tg);
+                    while (ok && tg != ptag) {
+                        if (clock64() - t0 > 20000000000LL) ok = false;          // ~10 s: dead peer
+                        ld_slot_sys(&mine->red[phase][lane][i], val, tg);
+                    }
+                    r[i] = val;
+                }
+            }
+            ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                double s0 = 0.0;
+                for (int q = 0; q < P; q++) s0 += __shfl_sync(0xffffffffu, r[i], q);
+                r[i] = s0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; i++) v[i] = r[i];
+    }
+    return ok;
+}
+
+// phase-end reduction + grid barrier of the persistent kernels; v[] = per-thread partial sums on entry, grid (and cross-rank)
+// sums in thread 0 on return.  SYNC 0: block sums, arrival counter, last CTA reduces and broadcasts (pcg_sync);
+// SYNC 1: all-to-all slots (pcg_sync_a2a).
+template <int NV, int SYNC>
+__device__ __forceinline__ bool pcg_reduce(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
+                                           unsigned long long &epoch, unsigned long long seq, double *sh, double *s_bc, double *sh2)
+{
+    if (SYNC == 1) return pcg_sync_a2a<NV>(a, v, phase, ptag, epoch, seq, sh2);
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = block_sum(v[i], sh);
+    return pcg_sync<NV>(a, v, phase, ptag, epoch, sh, s_bc);
+}
+
 // FUSED: the direction phase (p = z + b p) and its grid barrier are folded into the SpMV: every gathered entry is formed
 // on the fly as fma(b, p_old[c], z[c]) from the previous direction (p is double-buffered), the halo push forms its values
 // the same way, and the row's own entry is written out as the new direction.  Two barriers per iteration instead of three
 // at the price of a second gather stream (L2-resident once the rows are split over several GPUs).
-template <int THREADS, int MINB, bool FUSED>
+template <int THREADS, int MINB, bool FUSED, int SYNC>
 __global__ void __launch_bounds__(THREADS, MINB)
 cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
 {
     __shared__ double sh[64];
     __shared__ double s_bc[4];
     __shared__ double s_push;
+    __shared__ double sh2[SYNC == 1 ? 384 : 1];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int nloc = a.nloc;
@@ -911,10 +1036,8 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
             a.dinv[i] = di; a.x[i] = 0.0; a.r[i] = ri; a.z[i] = zi;
             zz += zi * zi; zr += zi * ri;
         }
-        double v[2];
-        v[0] = block_sum(zz, sh);
-        v[1] = block_sum(zr, sh);
-        const bool ok = pcg_sync<2>(a, v, 1, ls.seq << 32, epoch, sh, s_bc);
+        double v[2] = {zz, zr};
+        const bool ok = pcg_reduce<2, SYNC>(a, v, 1, ls.seq << 32, epoch, ls.seq, sh, s_bc, sh2);
         zz = v[0]; zr = v[1];
         if (threadIdx.x == 0) {
             step_after_setup(&ls, zz, zr);
@@ -943,8 +1066,8 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
                 p2[i] = pv;
             }
             if ((nloc & 1) && gtid == 0) a.p[nloc - 1] = first ? a.z[nloc - 1] : a.z[nloc - 1] + b * a.p[nloc - 1];
-            double none[1];
-            pcg_sync<0>(a, none, 0, 0ULL, epoch, sh, s_bc);
+            double none[1] = {0.0};
+            pcg_reduce<0, SYNC>(a, none, 0, 0ULL, epoch, ls.seq, sh, s_bc, sh2);
         }
         auto pval = [&](int c) -> double {     // entry c of the current direction
             if (!FUSED) return a.p[c];
@@ -1016,10 +1139,10 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
                     pw = fma(pr, sum, pw);
                 }
             }
-            double v[1];
-            v[0] = block_sum(pw, sh);
+            double v[1] = {pw};
             if (!halo_ok) v[0] = __longlong_as_double(0x7ff8000000000000LL);
-            const bool ok = pcg_sync<1>(a, v, 0, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 2u), epoch, sh, s_bc);
+            const bool ok = pcg_reduce<1, SYNC>(a, v, 0, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 2u), epoch,
+                                                ls.seq, sh, s_bc, sh2);
             pw = v[0];
             if (threadIdx.x == 0) {
                 step_after_spmv(&ls, pw);
@@ -1052,10 +1175,9 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
                 a.x[i] = xv; a.r[i] = rv; a.z[i] = zv;
                 zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
             }
-            double v[2];
-            v[0] = block_sum(zz, sh);
-            v[1] = block_sum(zr, sh);
-            const bool ok = pcg_sync<2>(a, v, 1, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 3u), epoch, sh, s_bc);
+            double v[2] = {zz, zr};
+            const bool ok = pcg_reduce<2, SYNC>(a, v, 1, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 3u), epoch,
+                                                ls.seq, sh, s_bc, sh2);
             zz = v[0]; zr = v[1];
             if (threadIdx.x == 0) {
                 step_after_update(&ls, zz, zr);
@@ -1111,13 +1233,14 @@ __device__ void step_sr(CgState *st, bool first, double zz, double zr, double zs
     begin_iteration_sr(st);
 }
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, int SYNC>
 __global__ void __launch_bounds__(THREADS, MINB)
 cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
 {
     __shared__ double sh[64];
     __shared__ double s_bc[4];
     __shared__ double s_push;
+    __shared__ double sh2[SYNC == 1 ? 384 : 1];
     __shared__ CgState ls;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
@@ -1148,8 +1271,8 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
     unsigned int round = 0;
     while (true) {
         {
-            double none[1];
-            pcg_sync<0>(a, none, 0, 0ULL, epoch, sh, s_bc);
+            double none[1] = {0.0};
+            pcg_reduce<0, SYNC>(a, none, 0, 0ULL, epoch, ls.seq, sh, s_bc, sh2);
         }
         // ---- halo push of z (nranks > 1) ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * round + 1u);
@@ -1214,12 +1337,10 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
                 zz = fma(zi, zi, zz); zr = fma(zi, ri, zr); zs = fma(zi, sum, zs);
             }
         }
-        double v[3];
-        v[0] = block_sum(zz, sh);
-        v[1] = block_sum(zr, sh);
-        v[2] = block_sum(zs, sh);
+        double v[3] = {zz, zr, zs};
         if (!halo_ok) v[0] = __longlong_as_double(0x7ff8000000000000LL);
-        const bool ok = pcg_sync<3>(a, v, (int)(round & 1u), (ls.seq << 32) | (unsigned long long)(4u * round + 2u), epoch, sh, s_bc);   // mailbox parity: see p2p_allreduce
+        const bool ok = pcg_reduce<3, SYNC>(a, v, (int)(round & 1u), (ls.seq << 32) | (unsigned long long)(4u * round + 2u), epoch,
+                                            ls.seq, sh, s_bc, sh2);   // mailbox parity: see p2p_allreduce
         if (threadIdx.x == 0) {
             step_sr(&ls, first, v[0], v[1], v[2]);
             if (!ok || v[0] != v[0]) ls.reason = -101;
@@ -1285,12 +1406,19 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     // 20 %, so it is off by default.
     const char *fenv = getenv("PFEM_PCG_FUSED");
     const bool fused = fenv ? (fenv[0] == '1') : false;
-#define PCG_PICK(T, M) (sr ? (const void *)cg_persistent_sr_kernel<T, M> : fused ? (const void *)cg_persistent_kernel<T, M, true> : (const void *)cg_persistent_kernel<T, M, false>)
+    // barrier flavour: all-to-all tagged slots (one hop) where the barrier latency matters (small per-GPU blocks: the
+    // 1024 x 1 shape), arrival counter + last-CTA reduction for the 5 x 256 shape (740 CTAs polling 740 slots each is
+    // no cheaper there, and that shape is bandwidth-bound).  PFEM_PCG_SYNC=a2a|last overrides.
+    const char *syenv = getenv("PFEM_PCG_SYNC");
+    const bool a2a = syenv ? (strcmp(syenv, "a2a") == 0) : (threads * minb <= 1280 && minb <= 2);
+#define PCG_PICK2(T, M, S) (sr ? (const void *)cg_persistent_sr_kernel<T, M, S> : fused ? (const void *)cg_persistent_kernel<T, M, true, S> : (const void *)cg_persistent_kernel<T, M, false, S>)
+#define PCG_PICK(T, M) (a2a ? PCG_PICK2(T, M, 1) : PCG_PICK2(T, M, 0))
     if (threads == 256 && minb == 5) fn = PCG_PICK(256, 5);
     else if (threads == 1024 && minb == 1) fn = PCG_PICK(1024, 1);
     else if (threads == 640 && minb == 2) fn = PCG_PICK(640, 2);
     else if (threads == 512 && minb == 2) fn = PCG_PICK(512, 2);
     else { set_error("PFEM_PCG_CFG: unsupported shape %dx%d", threads, minb); return PFEM_ERR_ARG; }
+#undef PCG_PICK2
 #undef PCG_PICK
     int per_sm = 0;
     PFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, threads, 0, 0));
@@ -1298,6 +1426,10 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     const int grid = h->sm_count * minb;
     cudaStream_t s = h->stream;
     if (!h->pcg_bcast.p) PFEM_TRY(h->pcg_bcast.alloc(16));
+    if (a2a && !h->pcg_a2a.p) {           // tags carry the solve sequence number: cleared once, never again
+        PFEM_TRY(h->pcg_a2a.alloc((size_t)2 * 3 * h->sm_count * 16 * 2));
+        PFEM_CUDA(cudaMemsetAsync(h->pcg_a2a.p, 0, h->pcg_a2a.n * sizeof(double), s));
+    }
     PFEM_CUDA(cudaMemsetAsync(h->pcg_bcast.p, 0, 16 * sizeof(double), s));
     PcgArgs a;
     memset(&a, 0, sizeof a);
@@ -1311,6 +1443,7 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     a.partials = h->partials.p; a.st = h->cg.p; a.ctx = a.multi ? h->p2p_ctx.p : nullptr;
     a.send_idx = h->send_idx.p; a.send_dst = h->send_dst.p;
     a.bcast = h->pcg_bcast.p;
+    a.a2a = h->pcg_a2a.p;
     a.arrive = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 8);
     a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 12);
     double *svp = h->sv.p;

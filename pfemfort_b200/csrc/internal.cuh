@@ -174,6 +174,7 @@ struct pfem_solver {
     pfem::DevBuf<int> brow_ids, brow_ptr, bcol;   // boundary row ids (local), ptr, compact ghost index
     pfem::DevBuf<int> off_ptr;                    // [size_local+1] per-row pointer into bcol/bval (persistent CG kernel)
     pfem::DevBuf<double> pcg_bcast;               // persistent kernel: locally broadcast reduction results + flag + push ticket
+    pfem::DevBuf<double> pcg_a2a;                 // persistent kernel, all-to-all barrier: tagged per-CTA slots
     pfem::DevBuf<double> bval;
     pfem::DevBuf<int> csr2sell;            // per CSR slot: destination (>=0 SELL entry, <0: -(offdiag entry)-1)
     std::vector<int> ghost_cols;           // global ids (sorted): PETSc garray

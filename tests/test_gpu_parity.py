@@ -268,36 +268,53 @@ def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch):
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
+# (PFEM_CG, PFEM_CG_SR, PFEM_PCG_FUSED, PFEM_PCG_SYNC, PFEM_PCG_CFG); entry 1 is the launch-per-phase reference point
+CG_VARIANTS = (("persistent", "0", "0", "", ""), ("kernels", "0", "0", "", ""), ("persistent", "1", "0", "", ""),
+               ("persistent", "0", "1", "", ""), ("persistent", "0", "0", "last", "1024x1"), ("persistent", "0", "0", "a2a", "1024x1"),
+               ("persistent", "0", "0", "a2a", "256x5"), ("persistent", "1", "0", "a2a", "512x2"), ("persistent", "0", "1", "last", "256x5"))
+
+
+def _set_cg_variant(monkeypatch, v):
+    mode, sr, fused, sync, cfg = v
+    monkeypatch.setenv("PFEM_CG", mode)
+    monkeypatch.setenv("PFEM_CG_SR", sr)     # 1: PETSc's single-reduction recurrences
+    monkeypatch.setenv("PFEM_PCG_FUSED", fused)   # 1: direction folded into the SpMV
+    for key, val in (("PFEM_PCG_SYNC", sync), ("PFEM_PCG_CFG", cfg)):   # barrier flavour / CTA shape of the persistent kernel
+        if val:
+            monkeypatch.setenv(key, val)
+        else:
+            monkeypatch.delenv(key, raising=False)
+
+
 def test_persistent_and_multi_kernel_cg_agree(gpu, input_dir, monkeypatch):
-    """The persistent cooperative CG kernel (default) and the launch-per-phase path follow the same PETSc
-    semantics: same reason, same iteration count, same solution to rounding."""
+    """The persistent cooperative CG kernel (default; both barrier flavours, every CTA shape) and the launch-per-phase
+    path follow the same PETSc semantics: same reason, same iteration count, same solution to rounding."""
     for name in ("tet10", "cookmembranetria32"):
         m, kind = _load(name, input_dir)
         num = D.number(m, kind)
         res = []
-        for mode, sr, fused in (("persistent", "0", "0"), ("kernels", "0", "0"), ("persistent", "1", "0"), ("persistent", "0", "1")):
-            monkeypatch.setenv("PFEM_CG", mode)
-            monkeypatch.setenv("PFEM_CG_SR", sr)     # 1: PETSc's single-reduction recurrences
-            monkeypatch.setenv("PFEM_PCG_FUSED", fused)   # 1: direction folded into the SpMV (default for nranks > 1)
+        for v in CG_VARIANTS:
+            _set_cg_variant(monkeypatch, v)
             s = S.SolverB200(0)
             info = D.run_rank(s, m, num, rtol=1e-10)
             res.append((info["its"], info["reason"], s.get_solution()))
+            info2 = D.run_rank(s, m, num, rtol=1e-10)          # a second solve on the same handle (tags carry the solve number)
+            assert (info2["its"], info2["reason"]) == (info["its"], info["reason"])
+            assert np.array_equal(s.get_solution(), res[-1][2]), "run-to-run determinism"
             s.free()
-        assert res[0][1] == res[1][1] == res[2][1] == res[3][1] == 2
-        assert abs(res[0][0] - res[1][0]) <= 1 and abs(res[3][0] - res[1][0]) <= 1
-        assert abs(res[2][0] - res[1][0]) <= max(1, ITS_TOL * res[1][0])
-        for k in (0, 2, 3):
-            assert np.abs(res[k][2] - res[1][2]).max() <= 1e-8 * np.abs(res[1][2]).max()
-    # max_it reached -> DIVERGED_ITS (-3) with its = max_it, on both paths
+        assert all(r[1] == 2 for r in res)
+        for k, v in enumerate(CG_VARIANTS):
+            tol = max(1, ITS_TOL * res[1][0]) if v[1] == "1" else 1
+            assert abs(res[k][0] - res[1][0]) <= tol, (v, res[k][0], res[1][0])
+            assert np.abs(res[k][2] - res[1][2]).max() <= 1e-8 * np.abs(res[1][2]).max(), v
+    # max_it reached -> DIVERGED_ITS (-3) with its = max_it, on every path
     m, kind = _load("tet10", input_dir)
     num = D.number(m, kind)
-    for mode, sr, fused in (("persistent", "0", "0"), ("kernels", "0", "0"), ("persistent", "1", "0"), ("persistent", "0", "1")):
-        monkeypatch.setenv("PFEM_CG", mode)
-        monkeypatch.setenv("PFEM_CG_SR", sr)
-        monkeypatch.setenv("PFEM_PCG_FUSED", fused)
+    for v in CG_VARIANTS:
+        _set_cg_variant(monkeypatch, v)
         s = S.SolverB200(0)
         info = D.run_rank(s, m, num, rtol=1e-10, max_it=7)
-        assert (info["its"], info["reason"]) == (7, -3)
+        assert (info["its"], info["reason"]) == (7, -3), v
         s.free()
 
 
