@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 
 RTOL = 1e-10
 TUNING_ENV = ("PFEM_ASM", "PFEM_CG", "PFEM_CG_SR", "PFEM_PCG_CFG", "PFEM_PCG_FUSED", "PFEM_KERNELS_P2P", "PFEM_TILE_ROWS",
-              "PFEM_TILE_THREADS", "PFEM_SYNC", "PFEM_ARITH")
+              "PFEM_TILE_THREADS", "PFEM_SYNC", "PFEM_ARITH", "PFEM_PCG_SYNC", "PFEM_PCG_HALO")
 
 
 def parse():

@@ -165,7 +165,14 @@ int main(int argc, char **argv)
     CHECK(pfem_solver_initialise(solver, size_local, size_global, diag_nnz.data(), offdiag_nnz.data()));
     const double rtol = getenv("PFEM_KSP_RTOL") ? atof(getenv("PFEM_KSP_RTOL")) : 1e-5;
     const int max_it = getenv("PFEM_KSP_MAX_IT") ? atoi(getenv("PFEM_KSP_MAX_IT")) : 10000;
-    CHECK(pfem_solver_set_options(solver, rtol, -1.0, -1.0, max_it, PFEM_PC_JACOBI));
+    // options: like the Fortran PROGRAMs, from "petsc_options.dat" in the working directory (PetscInitialize, :168); the
+    // environment (PFEM_KSP_RTOL, PFEM_KSP_MAX_IT, PFEM_PC_TYPE=none|jacobi|bjacobi) overrides.  With neither, the reference's
+    // coded defaults apply: CG + PCBJACOBI/ILU(0), rtol 1e-5 (solverpetsc.F:187,206).
+    CHECK(pfem_solver_set_options_from_file(solver, "petsc_options.dat"));
+    int pc = -1;
+    if (const char *pcs = getenv("PFEM_PC_TYPE"))
+        pc = !strcmp(pcs, "none") ? PFEM_PC_NONE : !strcmp(pcs, "jacobi") ? PFEM_PC_JACOBI : PFEM_PC_BJACOBI_ILU0;
+    CHECK(pfem_solver_set_options(solver, getenv("PFEM_KSP_RTOL") ? rtol : -1.0, -1.0, -1.0, getenv("PFEM_KSP_MAX_IT") ? max_it : -1, pc));
     // the elements this rank hands to its GPU: owned + overlap (every element with a dof in its row block)
     std::vector<int> lconn = conn, ledof = edof;
     int nLocal = nElem;

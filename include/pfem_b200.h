@@ -41,7 +41,8 @@ enum {
 enum { PFEM_SOLVER_EMPTY = 1, PFEM_PATTERN_OK = 2, PFEM_INIT_OK = 3, PFEM_ASSEMBLY_OK = 4, PFEM_FACTORISE_OK = 5 };
 
 /* preconditioners (PCSetFromOptions, solverpetsc.F:202-210); the north-star run uses -pc_type jacobi */
-enum { PFEM_PC_NONE = 0, PFEM_PC_JACOBI = 1 };
+enum { PFEM_PC_NONE = 0, PFEM_PC_JACOBI = 1,
+       PFEM_PC_BJACOBI_ILU0 = 2 /* the reference's default: PCBJACOBI (solverpetsc.F:206), one block per rank, sub-PC ILU(0) */ };
 
 /* value-pass kernel selection (pfem_solver_set_assembly_mode; the environment variable PFEM_ASM overrides it) */
 enum { PFEM_ASM_AUTO = 0, PFEM_ASM_ROWS = 1, PFEM_ASM_FAST = 2 };
@@ -59,7 +60,8 @@ enum { PFEM_POISSON_TRIA = 0, PFEM_POISSON_TETRA = 1, PFEM_ELASTICITY_TRIA = 2, 
 enum {
     PFEM_CONVERGED_RTOL = 2, PFEM_CONVERGED_ATOL = 3, PFEM_CONVERGED_ITS = 4,
     PFEM_DIVERGED_ITS = -3, PFEM_DIVERGED_DTOL = -4, PFEM_DIVERGED_INDEFINITE_PC = -8,
-    PFEM_DIVERGED_NANORINF = -9, PFEM_DIVERGED_INDEFINITE_MAT = -10
+    PFEM_DIVERGED_NANORINF = -9, PFEM_DIVERGED_INDEFINITE_MAT = -10,
+    PFEM_DIVERGED_PCSETUP_FAILED = -11 /* zero pivot in ILU(0) */
 };
 
 const char *pfem_last_error(void);
@@ -108,6 +110,11 @@ int pfem_solver_initialise(pfem_solver_t *h, int size_local, int size_global, co
                            const int *offdiag_nnz);
 /* KSPSetFromOptions / PCSetFromOptions, solverpetsc.F:190-210 (-ksp_rtol -ksp_atol -ksp_divtol -ksp_max_it -pc_type) */
 int pfem_solver_set_options(pfem_solver_t *h, double rtol, double abstol, double dtol, int max_it, int pc_type);
+/* PetscInitialize(PETSC_NULL_CHARACTER "petsc_options.dat") + KSPSetFromOptions/PCSetFromOptions
+   (tetrapoissonparallelimpl1.F:168, solverpetsc.F:190-210): -ksp_rtol -ksp_atol -ksp_divtol -ksp_max_it -ksp_type cg
+   -pc_type none|jacobi|bjacobi [-sub_pc_type ilu]; a missing file leaves the coded defaults (CG + PCBJACOBI/ILU(0),
+   rtol 1e-5), an unsupported KSP/PC type is PFEM_ERR_ARG.  In pfem_solver_set_options negative values mean "keep". */
+int pfem_solver_set_options_from_file(pfem_solver_t *h, const char *path);
 
 /* The mesh arrays the element loop reads (tetrapoissonparallelimpl1.F:832-838): uploaded once and kept
  * resident in HBM.  conn holds NEW node ids; coords stay in OLD numbering and are reached through
@@ -169,6 +176,10 @@ int pfem_solver_set_rhs(pfem_solver_t *h, const double *rhs_local);
 /* owned rows of the assembled matrix: rowptr[size_local+1], col[nnz] (global), val[nnz]; any may be NULL */
 int pfem_solver_get_nnz(pfem_solver_t *h, long long *nnz);
 int pfem_solver_get_csr(pfem_solver_t *h, int *rowptr, int *col, double *val);
+/* diagnostics: ILU(0) factor of the last PCBJACOBI solve (PCSetUp_ILU inside KSPSolve, solverpetsc.F:476) on the CSR slots
+   of the local rows (unit-lower multipliers below the diagonal, U on and above it, slots outside the diagonal block keep
+   the matrix value) and the inverted pivots [size_local] */
+int pfem_solver_get_ilu_factor(pfem_solver_t *h, double *fval, double *invdiag);
 /* KSPGetIterationNumber / KSPGetConvergedReason (solverpetsc.F:479-488) and the two timers the drivers
  * print (tetrapoissonparallelimpl1.F:893-905), measured with CUDA events on the library's stream */
 int pfem_solver_get_info(pfem_solver_t *h, int *its, int *reason, double *rnorm, double *t_assemble_s,

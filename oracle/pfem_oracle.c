@@ -704,6 +704,127 @@ ORC_API int orc_cg_jacobi(int N, const int *rowptr, const int *col, const double
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* KSPSolve with the reference's DEFAULT preconditioner: CG + PCBJACOBI (solverpetsc.F:187,206),   */
+/* i.e. one block per MPI rank = the rank's diagonal block [block_start[b], block_start[b+1]),     */
+/* sub-KSP preonly, sub-PC ILU(0) in natural ordering (PETSc defaults; PETSc 3.6.4 is not in the   */
+/* tree: algorithm restated from MatLUFactorNumeric_SeqAIJ / MatSolve_SeqAIJ).                     */
+/*   factor (row i, IKJ): for k in L(i) ascending: m = a_ik * (1/u_kk); a_ik = m;                  */
+/*                         for j in U(k), j > k, j in pattern(i): a_ij -= m * u_kj                 */
+/*                         pivot stored inverted (zero pivot -> reason -11)                        */
+/*   solve: forward  y_i = r_i - sum_{j in L(i)} l_ij y_j   (ascending j)                          */
+/*          backward z_i = (y_i - sum_{j in U(i), j > i} u_ij z_j) * (1/u_ii)   (ascending j)      */
+/* Entries outside the block are ignored by the preconditioner (block Jacobi).                     */
+/* ------------------------------------------------------------------------- */
+
+ORC_API int orc_ilu0_factor(int N, const int *rowptr, const int *col, const double *val, int nblocks,
+                            const int *block_start, double *fval, double *invdiag)
+{
+    /* fval: factor values on the CSR slots (slots outside the diagonal blocks keep the matrix value, unused) */
+    memcpy(fval, val, sizeof(double) * (size_t)rowptr[N]);
+    for (int b = 0; b < nblocks; b++) {
+        const int lo = block_start[b], hi = block_start[b + 1];
+        for (int i = lo; i < hi; i++) {
+            long long di = -1;
+            for (int q = rowptr[i]; q < rowptr[i + 1]; q++) {
+                const int k = col[q];
+                if (k < lo) continue;
+                if (k >= i) { if (k == i) di = q; break; }
+                const double m = fval[q] * invdiag[k];
+                fval[q] = m;
+                /* merge U(k) (cols > k of row k, inside the block) into row i */
+                int qi = q + 1;
+                for (int qk = rowptr[k]; qk < rowptr[k + 1]; qk++) {
+                    const int j = col[qk];
+                    if (j <= k) continue;
+                    if (j >= hi) break;
+                    while (qi < rowptr[i + 1] && col[qi] < j) qi++;
+                    if (qi < rowptr[i + 1] && col[qi] == j) fval[qi] = fval[qi] - m * fval[qk];
+                }
+            }
+            if (di < 0 || fval[di] == 0.0) return -11;      /* missing or zero pivot */
+            invdiag[i] = 1.0 / fval[di];
+        }
+    }
+    return 0;
+}
+
+ORC_API void orc_ilu0_solve(int N, const int *rowptr, const int *col, const double *fval, const double *invdiag,
+                            int nblocks, const int *block_start, const double *r, double *z)
+{
+    for (int b = 0; b < nblocks; b++) {
+        const int lo = block_start[b], hi = block_start[b + 1];
+        for (int i = lo; i < hi; i++) {
+            double sum = r[i];
+            for (int q = rowptr[i]; q < rowptr[i + 1]; q++) {
+                const int j = col[q];
+                if (j < lo) continue;
+                if (j >= i) break;
+                sum = sum - fval[q] * z[j];
+            }
+            z[i] = sum;
+        }
+        for (int i = hi - 1; i >= lo; i--) {
+            double sum = z[i];
+            for (int q = rowptr[i]; q < rowptr[i + 1]; q++) {
+                const int j = col[q];
+                if (j <= i) continue;
+                if (j >= hi) break;
+                sum = sum - fval[q] * z[j];
+            }
+            z[i] = sum * invdiag[i];
+        }
+    }
+}
+
+ORC_API int orc_cg_bjacobi_ilu0(int N, const int *rowptr, const int *col, const double *val, const double *b,
+                                double *x, int nblocks, const int *block_start, double rtol, double abstol, double dtol,
+                                int max_it, int *its_out, int *reason_out, double *rnorm_out)
+{
+    double *r = malloc(sizeof(double) * (size_t)N), *z = malloc(sizeof(double) * (size_t)N);
+    double *p = malloc(sizeof(double) * (size_t)N), *w = malloc(sizeof(double) * (size_t)N);
+    double *invdiag = malloc(sizeof(double) * (size_t)N), *fval = malloc(sizeof(double) * (size_t)(rowptr[N] > 0 ? rowptr[N] : 1));
+    int its = 0, reason = orc_ilu0_factor(N, rowptr, col, val, nblocks, block_start, fval, invdiag);
+    double dp = 0.0, ttol = 0, rnorm0 = 0;
+    for (int i = 0; i < N; i++) { x[i] = 0.0; r[i] = b[i]; }
+    if (!reason) {
+        orc_ilu0_solve(N, rowptr, col, fval, invdiag, nblocks, block_start, r, z);
+        dp = sqrt(dot(N, z, z, 1));
+        reason = converged_default(0, dp, rtol, abstol, dtol, &ttol, &rnorm0);
+    }
+    if (!reason) {
+        double beta = dot(N, z, r, 1), betaold = 0.0, dpi = 0.0, dpiold;
+        int i = 0;
+        do {
+            its = i + 1;
+            if (beta == 0.0) { reason = 3; break; }
+            if (i > 0 && beta * betaold < 0.0) { reason = -8; break; }
+            if (i == 0) memcpy(p, z, sizeof(double) * (size_t)N);
+            else {
+                double bb = beta / betaold;
+                for (int k = 0; k < N; k++) p[k] = z[k] + bb * p[k];
+            }
+            dpiold = dpi;
+            spmv(N, rowptr, col, val, p, w, 1);
+            dpi = dot(N, p, w, 1);
+            betaold = beta;
+            if (dpi == 0.0 || (i > 0 && dpi * dpiold <= 0.0)) { reason = -10; break; }
+            double a = beta / dpi;
+            for (int k = 0; k < N; k++) { x[k] = x[k] + a * p[k]; r[k] = r[k] - a * w[k]; }
+            orc_ilu0_solve(N, rowptr, col, fval, invdiag, nblocks, block_start, r, z);
+            dp = sqrt(dot(N, z, z, 1));
+            reason = converged_default(i + 1, dp, rtol, abstol, dtol, &ttol, &rnorm0);
+            if (reason) break;
+            beta = dot(N, z, r, 1);
+            i++;
+        } while (i < max_it);
+        if (!reason && i >= max_it) reason = -3;
+    }
+    *its_out = its; *reason_out = reason; *rnorm_out = dp;
+    free(r); free(z); free(p); free(w); free(invdiag); free(fval);
+    return 0;
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP

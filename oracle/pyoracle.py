@@ -162,5 +162,35 @@ def cg_jacobi(rowptr, col, val, b, rtol=1e-5, abstol=1e-50, dtol=1e4, max_it=100
     return x, its.value, reason.value, rnorm.value
 
 
+def cg_bjacobi_ilu0(rowptr, col, val, b, block_start=None, rtol=1e-5, abstol=1e-50, dtol=1e4, max_it=10000):
+    """KSPCG + PCBJACOBI/ILU(0): the reference's default (solverpetsc.F:187,206).  block_start: row ranges of the ranks
+    (one block per rank), default one block."""
+    N = len(rowptr) - 1
+    bs = _i32(np.array([0, N] if block_start is None else block_start))
+    x = np.zeros(N)
+    its, reason, rn = C.c_int(0), C.c_int(0), C.c_double(0)
+    lib().orc_cg_bjacobi_ilu0(N, _i(rowptr), _i(col), _d(val), _d(b), _d(x), len(bs) - 1, _i(bs), C.c_double(rtol),
+                              C.c_double(abstol), C.c_double(dtol), max_it, C.byref(its), C.byref(reason),
+                              C.byref(rn))
+    return x, its.value, reason.value, rn.value
+
+
+def ilu0_factor(rowptr, col, val, block_start=None):
+    N = len(rowptr) - 1
+    bs = _i32(np.array([0, N] if block_start is None else block_start))
+    fval = np.zeros(len(col))
+    invd = np.zeros(N)
+    rc = lib().orc_ilu0_factor(N, _i(rowptr), _i(col), _d(val), len(bs) - 1, _i(bs), _d(fval), _d(invd))
+    return fval, invd, rc
+
+
+def ilu0_solve(rowptr, col, fval, invdiag, r, block_start=None):
+    N = len(rowptr) - 1
+    bs = _i32(np.array([0, N] if block_start is None else block_start))
+    z = np.zeros(N)
+    lib().orc_ilu0_solve(N, _i(rowptr), _i(col), _d(fval), _d(invdiag), len(bs) - 1, _i(bs), _d(np.ascontiguousarray(r, np.float64)), _d(z))
+    return z
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -192,7 +192,8 @@ int pfem_solver_initialise(pfem_solver_t *h, int size_local, int size_global, co
     }
     h->size_local = size_local; h->size_global = size_global;
     h->row_lo = h->row_starts[h->rank]; h->row_hi = h->row_starts[h->rank + 1];
-    h->rtol = 1e-5; h->abstol = 1e-50; h->dtol = 1e4; h->max_it = 10000; h->pc_type = PFEM_PC_JACOBI;
+    h->rtol = 1e-5; h->abstol = 1e-50; h->dtol = 1e4; h->max_it = 10000;
+    h->pc_type = PFEM_PC_BJACOBI_ILU0;  // solverpetsc.F:206 PCSetType(PCBJACOBI): the reference's default unless the options say otherwise
     h->state = PFEM_SOLVER_EMPTY;       // solverpetsc.F:212
     h->initialised = true;
     h->have_dofs = false;
@@ -203,13 +204,50 @@ int pfem_solver_initialise(pfem_solver_t *h, int size_local, int size_global, co
 int pfem_solver_set_options(pfem_solver_t *h, double rtol, double abstol, double dtol, int max_it, int pc_type)
 {
     PFEM_TRY(need_handle(h, "pfem_solver_set_options"));
-    if (pc_type != PFEM_PC_NONE && pc_type != PFEM_PC_JACOBI) { set_error("pc_type %d not supported (none|jacobi)", pc_type); return PFEM_ERR_ARG; }
+    if (pc_type >= 0 && pc_type != PFEM_PC_NONE && pc_type != PFEM_PC_JACOBI && pc_type != PFEM_PC_BJACOBI_ILU0) {
+        set_error("pc_type %d not supported (none|jacobi|bjacobi)", pc_type);
+        return PFEM_ERR_ARG;
+    }
     if (rtol >= 0) h->rtol = rtol;
     if (abstol >= 0) h->abstol = abstol;
     if (dtol >= 0) h->dtol = dtol;
     if (max_it >= 0) h->max_it = max_it;
-    h->pc_type = pc_type;
+    if (pc_type >= 0) h->pc_type = pc_type;           // negative: keep (the default is the reference's PCBJACOBI/ILU(0))
     return PFEM_OK;
+}
+
+// PetscInitialize(..., "petsc_options.dat") + KSPSetFromOptions/PCSetFromOptions (tetrapoissonparallelimpl1.F:168,
+// solverpetsc.F:190-210): the subset of the PETSc options database this path understands.  Unknown options are ignored
+// like PETSc ignores unused ones; a KSP/PC type this library does not implement is an error, never a silent substitute.
+int pfem_solver_set_options_from_file(pfem_solver_t *h, const char *path)
+{
+    PFEM_TRY(need_handle(h, "pfem_solver_set_options_from_file"));
+    FILE *f = path ? fopen(path, "r") : nullptr;
+    if (!f) return PFEM_OK;                            // no options file: PETSc runs with the coded defaults
+    char line[512];
+    int rc = PFEM_OK;
+    while (rc == PFEM_OK && fgets(line, sizeof line, f)) {
+        char key[128] = "", val[256] = "";
+        char *hash = strchr(line, '#');
+        if (hash) *hash = 0;
+        if (sscanf(line, " %127s %255s", key, val) < 1 || key[0] != '-') continue;
+        if (!strcmp(key, "-ksp_rtol")) h->rtol = atof(val);
+        else if (!strcmp(key, "-ksp_atol")) h->abstol = atof(val);
+        else if (!strcmp(key, "-ksp_divtol")) h->dtol = atof(val);
+        else if (!strcmp(key, "-ksp_max_it")) h->max_it = atoi(val);
+        else if (!strcmp(key, "-ksp_type")) {
+            if (strcmp(val, "cg")) { set_error("%s: -ksp_type %s not supported (cg)", path, val); rc = PFEM_ERR_ARG; }
+        } else if (!strcmp(key, "-pc_type")) {
+            if (!strcmp(val, "jacobi")) h->pc_type = PFEM_PC_JACOBI;
+            else if (!strcmp(val, "none")) h->pc_type = PFEM_PC_NONE;
+            else if (!strcmp(val, "bjacobi")) h->pc_type = PFEM_PC_BJACOBI_ILU0;
+            else { set_error("%s: -pc_type %s not supported (none|jacobi|bjacobi)", path, val); rc = PFEM_ERR_ARG; }
+        } else if (!strcmp(key, "-sub_pc_type")) {
+            if (strcmp(val, "ilu")) { set_error("%s: -sub_pc_type %s not supported (ilu)", path, val); rc = PFEM_ERR_ARG; }
+        }
+    }
+    fclose(f);
+    return rc;
 }
 
 int pfem_solver_set_mesh(pfem_solver_t *h, int kind, int nElem, const int *conn, int nNode, const double *coords,
@@ -408,6 +446,19 @@ int pfem_solver_get_nnz(pfem_solver_t *h, long long *nnz)
 {
     PFEM_TRY(need_pattern(h, "pfem_solver_get_nnz"));
     if (nnz) *nnz = h->nnz;
+    return PFEM_OK;
+}
+
+// diagnostics: the ILU(0) factor of the last solve with pc_type = PFEM_PC_BJACOBI_ILU0, on the CSR slots of the local rows
+// (slots outside the diagonal block keep the matrix value) + the inverted pivots; parity tests compare them bit for bit
+int pfem_solver_get_ilu_factor(pfem_solver_t *h, double *fval, double *invdiag)
+{
+    PFEM_TRY(need_pattern(h, "pfem_solver_get_ilu_factor"));
+    if (!fval || !invdiag) { set_error("NULL output"); return PFEM_ERR_ARG; }
+    if (!h->ilu_fval.p || h->ilu_fval.n < (size_t)h->nnz || !h->ilu_invd.p) { set_error("pfem_solver_get_ilu_factor: no ILU(0) factor yet"); return PFEM_ERR_STATE; }
+    PFEM_CUDA(cudaMemcpyAsync(fval, h->ilu_fval.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PFEM_CUDA(cudaMemcpyAsync(invdiag, h->ilu_invd.p, (size_t)h->size_local * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    PFEM_CUDA(cudaStreamSynchronize(h->stream));
     return PFEM_OK;
 }
 

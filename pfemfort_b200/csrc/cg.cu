@@ -96,6 +96,28 @@ __device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v)
     asm volatile("st.global.relaxed.sys.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 
+// Tag-validated halo entries: the sender writes {value, tag} with ONE 16-byte store over NVLink, the consumer spins on the
+// entry it needs until the tag is this iteration's.  No fence, no flag, no ticket: a rank never waits for data it does not
+// read, and nobody waits for the sender's remote stores to be acknowledged.
+__device__ __forceinline__ void st_ghost_tagged(double *p, double v, unsigned long long tag)
+{
+    asm volatile("st.global.relaxed.sys.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ double ld_ghost_tagged(const double *p, unsigned long long tag, bool &ok)
+{
+    long long bits;
+    unsigned long long tg;
+    asm volatile("ld.global.relaxed.sys.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+    if (tg != tag) {
+        const long long t0 = clock64();
+        do {
+            if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a dead peer must not hang the GPU
+            asm volatile("ld.global.relaxed.sys.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+        } while (tg != tag);
+    }
+    return __longlong_as_double(bits);
+}
+
 __device__ __forceinline__ unsigned long long p2p_tag(const CgState *st, int kind)
 {
     return (st->seq << 32) | (unsigned long long)(4u * (unsigned int)st->iter + (unsigned int)kind);
@@ -431,8 +453,12 @@ int build_solver_structures(pfem_solver *h)
         std::vector<int> sync;
         PFEM_TRY(comm_allgather_int(h, 0, sync));
     }
-    PFEM_TRY(h->ghost_buf.alloc((size_t)h->n_ghost + 1));
-    PFEM_TRY(h->partials.alloc((size_t)4 * h->sm_count * 16));
+    // [0, n_ghost]: plain ghost values (NCCL / flag-synchronised halo); from ghost_tag_off on: 16-byte {value, tag} entries
+    // of the tag-validated halo (persistent kernel).  One allocation = one IPC handle.
+    h->ghost_tag_off = ((size_t)h->n_ghost + 2) & ~(size_t)1;
+    PFEM_TRY(h->ghost_buf.alloc(h->ghost_tag_off + 2 * ((size_t)h->n_ghost + 1)));
+    PFEM_CUDA(cudaMemsetAsync(h->ghost_buf.p, 0, h->ghost_buf.n * sizeof(double), h->stream));
+    PFEM_TRY(h->partials.alloc((size_t)8 * h->sm_count * 16));     // pcg_sync_ctr: [2 epoch parities][3 values][pstride]
     if (!h->cg.p) {
         PFEM_TRY(h->cg.alloc(1));
         PFEM_CUDA(cudaMemsetAsync(h->cg.p, 0, sizeof(CgState), s));
@@ -490,11 +516,19 @@ cg_setup_kernel(int nloc, int row_lo, int pc_type, const int *__restrict__ rowpt
                 const double *__restrict__ val, const double *__restrict__ b, double *__restrict__ x,
                 double *__restrict__ r, double *__restrict__ z, double *__restrict__ dinv, double *__restrict__ partials,
                 int pstride, CgState *st, int finalize /*0: publish red, 1: finalise, 2: peer all-reduce + finalise*/,
-                const P2pCtx *ctx)
+                const P2pCtx *ctx, int stage /*0: everything; ILU(0): 1 = x, r only, 2 = (z.z, z.r) of the solved z only*/)
 {
     __shared__ double sh[64];
     double zz = 0.0, zr = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += gridDim.x * blockDim.x) {
+    if (stage == 1) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += gridDim.x * blockDim.x) { x[i] = 0.0; r[i] = b[i]; }
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc && stage == 2; i += gridDim.x * blockDim.x) {
+        const double zi = z[i], ri = r[i];
+        zz += zi * zi; zr += zi * ri;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc && stage == 0; i += gridDim.x * blockDim.x) {
         double d = 0.0;
         int lo = rowptr[i], hi = rowptr[i + 1];
         const int end = hi, c = row_lo + i;
@@ -694,13 +728,24 @@ __global__ void pack_halo_kernel(int n, const int *__restrict__ idx, const doubl
 __global__ void __launch_bounds__(CG_THREADS)
 cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__ w, const double *__restrict__ dinv,
                  double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *__restrict__ partials,
-                 int pstride, CgState *st, int finalize, const P2pCtx *ctx)
+                 int pstride, CgState *st, int finalize, const P2pCtx *ctx, int stage /*as cg_setup_kernel*/)
 {
     __shared__ double sh[64];
     if (st->reason != 0) return;
     const double a = st->a;
     double zz = 0.0, zr = 0.0;
-    const int n2 = n >> 1;
+    if (stage == 1) {          // x += a p ; r -= a w   (the ILU solves produce z)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            x[i] = fma(a, p[i], x[i]);
+            r[i] = fma(-a, w[i], r[i]);
+        }
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && stage == 2; i += gridDim.x * blockDim.x) {
+        const double zv = z[i], rv = r[i];
+        zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
+    }
+    const int n2 = stage == 2 ? 0 : n >> 1;
     const double2 *p2 = reinterpret_cast<const double2 *>(p), *w2 = reinterpret_cast<const double2 *>(w);
     const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
     double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r), *z2 = reinterpret_cast<double2 *>(z);
@@ -714,7 +759,7 @@ cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__
         zz = fma(zv.x, zv.x, zz); zz = fma(zv.y, zv.y, zz);
         zr = fma(zv.x, rv.x, zr); zr = fma(zv.y, rv.y, zr);
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (stage == 0 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int i = n - 1;
         const double xv = fma(a, p[i], x[i]), rv = fma(-a, w[i], r[i]), zv = rv * dinv[i];
         x[i] = xv; r[i] = rv; z[i] = zv;
@@ -743,6 +788,244 @@ cg_update_kernel(int n, const double *__restrict__ p, const double *__restrict__
 
 
 // =====================================================================================================================
+// PCBJACOBI + ILU(0): the reference's DEFAULT preconditioner (solverpetsc.F:206 PCSetType(PCBJACOBI); PETSc's default
+// sub-PC is ILU(0) in natural ordering, one block per rank = this rank's diagonal block).  Restated from PETSc 3.6
+// MatLUFactorNumeric_SeqAIJ / MatSolve_SeqAIJ (not in the tree); the CPU checker restates the same two routines.
+//
+// All three kernels are "synchronisation-free" (no level sets, no grid barriers): one warp owns one row, rows are handed
+// out in dependency order through a ticket taken when a CTA starts running -- so every row a warp waits for belongs to a
+// CTA that is already running or finished -- and a warp spins on exactly the rows it reads.
+//   factor : IKJ over the row's lower entries in ascending column order; the k-th update needs row k's U part (flag per
+//            row, release/acquire); the lanes update the row's remaining entries (binary search in the sorted row).
+//   solves : every value is published as ONE 16-byte {value, tag} store and consumers spin on the tagged value itself
+//            (no fence, no flag): a dependent hop costs one L2 store + one L2 load.
+// The arithmetic is the sequential algorithm's, operation for operation (explicit __dmul_rn/__dsub_rn: no FMA
+// contraction, ascending column order) => factor and preconditioned residuals are bit-identical to the oracle whatever
+// the schedule, and run-to-run deterministic.
+// =====================================================================================================================
+
+struct IluTagged { double v; unsigned long long tag; };
+
+__device__ __forceinline__ void st_tagged_gpu(IluTagged *p, double v, unsigned long long tag)
+{
+    asm volatile("st.global.relaxed.gpu.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ double ld_tagged_gpu(const IluTagged *p, unsigned long long tag, int *fail)
+{
+    long long bits;
+    unsigned long long tg;
+    asm volatile("ld.global.relaxed.gpu.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+    if (tg != tag) {
+        const long long t0 = clock64();
+        do {
+            if (clock64() - t0 > 20000000000LL) { *fail = 1; break; }      // ~10 s: never hang the GPU
+            asm volatile("ld.global.relaxed.gpu.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+        } while (tg != tag);
+    }
+    return __longlong_as_double(bits);
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.global.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.global.release.gpu.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// per row: first slot of the diagonal block, slot of the diagonal, end of the diagonal block (columns are sorted)
+__global__ void ilu_rows_kernel(int nloc, int row_lo, int row_hi, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                int *__restrict__ dlo, int *__restrict__ ddiag, int *__restrict__ dhi, int *__restrict__ bad)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += gridDim.x * blockDim.x) {
+        const int a = rowptr[i], b = rowptr[i + 1];
+        auto lower = [&](int key) {
+            int lo = a, hi = b;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (col[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            return lo;
+        };
+        const int l = lower(row_lo), d = lower(row_lo + i), h = lower(row_hi);
+        dlo[i] = l; dhi[i] = h;
+        ddiag[i] = (d < b && col[d] == row_lo + i) ? d : -1;
+        if (ddiag[i] < 0) atomicAdd(bad, 1);          // PETSc: "Matrix is missing diagonal entry"
+    }
+}
+
+static constexpr int ILU_WARPS = 8;
+static int grid_for(pfem_solver *h, long long work_items, int per_thread);
+
+// numeric ILU(0) of the diagonal block, in place on fval (a copy of the CSR values); invd = inverted pivots
+__global__ void __launch_bounds__(ILU_WARPS * 32)
+ilu_factor_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ dlo, const int *__restrict__ ddiag,
+                  const int *__restrict__ dhi, double *fval, double *invd, unsigned int *ready, unsigned int epoch,
+                  unsigned long long *ticket, unsigned long long ticket_base, CgState *st)
+{
+    __shared__ unsigned long long s_blk;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    if (i >= nloc) return;
+    const int q0 = dlo[i], qd = ddiag[i], q1 = dhi[i];
+    int fail = 0;
+    for (int q = q0; q < qd; q++) {
+        const int k = col[q] - row_lo;
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(ready + k) != epoch)
+                if (clock64() - t0 > 20000000000LL) { fail = 1; break; }
+        }
+        __syncwarp();
+        const double m = __dmul_rn(__ldcg(fval + q), __ldcg(invd + k));
+        __syncwarp();
+        if (lane == 0) __stcg(fval + q, m);
+        // U(k): columns > k of row k inside the block; each lands on a distinct entry of row i (or on none)
+        const int u0 = ddiag[k] + 1, u1 = dhi[k];
+        for (int t = u0 + lane; t < u1; t += 32) {
+            const int j = col[t];
+            int lo = q + 1, hi = q1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (col[mid] < j) lo = mid + 1; else hi = mid;
+            }
+            if (lo < q1 && col[lo] == j) __stcg(fval + lo, __dsub_rn(__ldcg(fval + lo), __dmul_rn(m, __ldcg(fval + t))));
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const double piv = __ldcg(fval + qd);
+        if (piv == 0.0 || fail) st->reason = fail ? -101 : PFEM_DIVERGED_PCSETUP_FAILED;     // zero pivot (no shift, PETSc default)
+        __stcg(invd + i, 1.0 / piv);
+        __threadfence();
+        st_release_gpu_u32(ready + i, epoch);
+    }
+}
+
+// forward substitution  y_i = r_i - sum_{j in L(i)} l_ij y_j   (ascending j)
+__global__ void __launch_bounds__(ILU_WARPS * 32)
+ilu_lower_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ dlo, const int *__restrict__ ddiag,
+                 const double *__restrict__ fval, const double *__restrict__ r, IluTagged *y, unsigned long long tag,
+                 unsigned long long *ticket, unsigned long long ticket_base, CgState *st)
+{
+    __shared__ unsigned long long s_blk;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
+    __syncthreads();
+    if (st->reason != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    if (i >= nloc) return;
+    const int q0 = dlo[i], qd = ddiag[i];
+    double sum = r[i];
+    int fail = 0;
+    for (int qb = q0; qb < qd; qb += 32) {
+        const int q = qb + lane;
+        double prod = 0.0;
+        if (q < qd) prod = __dmul_rn(fval[q], ld_tagged_gpu(y + (col[q] - row_lo), tag, &fail));
+        const int n = min(32, qd - qb);
+        for (int t = 0; t < n; t++) sum = __dsub_rn(sum, __shfl_sync(0xffffffffu, prod, t));
+    }
+    if (__any_sync(0xffffffffu, fail) && lane == 0) st->reason = -101;
+    if (lane == 0) st_tagged_gpu(y + i, sum, tag);
+}
+
+// backward substitution  z_i = (y_i - sum_{j in U(i), j > i} u_ij z_j) * (1/u_ii)   (ascending j), rows in descending order
+__global__ void __launch_bounds__(ILU_WARPS * 32)
+ilu_upper_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ ddiag, const int *__restrict__ dhi,
+                 const double *__restrict__ fval, const double *__restrict__ invd, const IluTagged *__restrict__ y,
+                 IluTagged *zt, double *__restrict__ z, unsigned long long tag, unsigned long long *ticket,
+                 unsigned long long ticket_base, CgState *st)
+{
+    __shared__ unsigned long long s_blk;
+    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
+    __syncthreads();
+    if (st->reason != 0) return;
+    const int lane = threadIdx.x & 31;
+    const long long ii = (long long)nloc - 1 - ((long long)s_blk * ILU_WARPS + (threadIdx.x >> 5));
+    if (ii < 0) return;
+    const int i = (int)ii;
+    const int q0 = ddiag[i] + 1, q1 = dhi[i];
+    double sum = y[i].v;                           // written by the forward kernel (kernel boundary)
+    int fail = 0;
+    for (int qb = q0; qb < q1; qb += 32) {
+        const int q = qb + lane;
+        double prod = 0.0;
+        if (q < q1) prod = __dmul_rn(fval[q], ld_tagged_gpu(zt + (col[q] - row_lo), tag, &fail));
+        const int n = min(32, q1 - qb);
+        for (int t = 0; t < n; t++) sum = __dsub_rn(sum, __shfl_sync(0xffffffffu, prod, t));
+    }
+    if (__any_sync(0xffffffffu, fail) && lane == 0) st->reason = -101;
+    if (lane == 0) {
+        const double zi = __dmul_rn(sum, invd[i]);
+        st_tagged_gpu(zt + i, zi, tag);
+        z[i] = zi;
+    }
+}
+
+// z = M^-1 r with M = ILU(0) of the diagonal block: two launches
+static int ilu_apply(pfem_solver *h)
+{
+    cudaStream_t s = h->stream;
+    const int nloc = h->size_local;
+    const unsigned int nblk = (unsigned int)((nloc + ILU_WARPS - 1) / ILU_WARPS);
+    if (nblk == 0) return PFEM_OK;
+    IluTagged *y = reinterpret_cast<IluTagged *>(h->ilu_y.p), *zt = reinterpret_cast<IluTagged *>(h->ilu_z.p);
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(h->ilu_ticket.p);
+    const unsigned long long tag = ++h->ilu_tag;
+    ilu_lower_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_dlo.p, h->ilu_ddiag.p, h->ilu_fval.p, h->r.p, y, tag,
+                                                     ticket, h->ilu_tickets, h->cg.p);
+    h->ilu_tickets += nblk;
+    ilu_upper_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_ddiag.p, h->ilu_dhi.p, h->ilu_fval.p, h->ilu_invd.p, y, zt,
+                                                     h->z.p, tag, ticket, h->ilu_tickets, h->cg.p);
+    h->ilu_tickets += nblk;
+    h->launches += 2;
+    return PFEM_OK;
+}
+
+// PCSetUp: diagonal-block row ranges + numeric factorisation
+static int ilu_setup(pfem_solver *h)
+{
+    cudaStream_t s = h->stream;
+    const int nloc = h->size_local;
+    const size_t n1 = (size_t)(nloc > 0 ? nloc : 1);
+    PFEM_TRY(h->ilu_dlo.alloc(n1)); PFEM_TRY(h->ilu_ddiag.alloc(n1)); PFEM_TRY(h->ilu_dhi.alloc(n1));
+    PFEM_TRY(h->ilu_fval.alloc((size_t)(h->nnz > 0 ? h->nnz : 1)));
+    PFEM_TRY(h->ilu_invd.alloc(n1));
+    if (!h->ilu_ticket.p) {
+        PFEM_TRY(h->ilu_ticket.alloc(2));
+        PFEM_CUDA(cudaMemsetAsync(h->ilu_ticket.p, 0, 2 * sizeof(double), s));
+        h->ilu_tickets = 0; h->ilu_tag = 0; h->ilu_epoch = 0;
+    }
+    if (h->ilu_y.n < 2 * n1 || h->ilu_ready.n < n1) {      // tags / epochs never repeat on a handle: cleared only when (re)allocated
+        PFEM_TRY(h->ilu_y.alloc(2 * n1)); PFEM_TRY(h->ilu_z.alloc(2 * n1)); PFEM_TRY(h->ilu_ready.alloc(n1));
+        PFEM_CUDA(cudaMemsetAsync(h->ilu_y.p, 0, h->ilu_y.n * sizeof(double), s));
+        PFEM_CUDA(cudaMemsetAsync(h->ilu_z.p, 0, h->ilu_z.n * sizeof(double), s));
+        PFEM_CUDA(cudaMemsetAsync(h->ilu_ready.p, 0, h->ilu_ready.n * sizeof(unsigned int), s));
+    }
+    if (nloc == 0) return PFEM_OK;
+    int *bad = reinterpret_cast<int *>(h->ilu_ticket.p + 1);
+    PFEM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
+    ilu_rows_kernel<<<grid_for(h, nloc, 1), CG_THREADS, 0, s>>>(nloc, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, h->ilu_dlo.p, h->ilu_ddiag.p,
+                                                              h->ilu_dhi.p, bad);
+    int nbad = 0;
+    PFEM_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaMemcpyAsync(h->ilu_fval.p, h->val.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    if (nbad) { set_error("ILU(0): %d rows of the diagonal block have no diagonal entry", nbad); return PFEM_ERR_STATE; }
+    const unsigned int nblk = (unsigned int)((nloc + ILU_WARPS - 1) / ILU_WARPS);
+    ilu_factor_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_dlo.p, h->ilu_ddiag.p, h->ilu_dhi.p, h->ilu_fval.p,
+                                                      h->ilu_invd.p, h->ilu_ready.p, ++h->ilu_epoch,
+                                                      reinterpret_cast<unsigned long long *>(h->ilu_ticket.p), h->ilu_tickets, h->cg.p);
+    h->ilu_tickets += nblk;
+    h->launches += 2;
+    return PFEM_OK;
+}
+
+// =====================================================================================================================
 // Persistent CG: the whole KSPSolve in ONE cooperative kernel per GPU.
 //
 // Kernel boundaries cost ~9 us each on this part (launch gap + last-CTA reduction tail), i.e. ~30 us of a 390 us
@@ -765,10 +1048,10 @@ struct PcgArgs {
     CgState *st;
     const P2pCtx *ctx;
     const int *send_idx; double *const *send_dst;
+    const double *ghost_t; double *const *send_dst_t; int halo_tag;   // tag-validated halo: 16-byte {value, tag} ghost entries
     double *bcast;                         // 4 PcgSlot {value, epoch}: [0..2] reduction results, [3] ok flag / release
     unsigned long long *arrive;            // monotonically increasing CTA arrival counter of the barriers
     unsigned int *push_ticket;             // monotonically increasing CTA arrival counter of the halo pushes
-    double *a2a;                           // all-to-all barrier: PcgSlot [2 parities][3 values][pstride] (pcg_sync_a2a)
 };
 
 __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
@@ -869,31 +1152,43 @@ __device__ __forceinline__ bool pcg_sync(const PcgArgs &a, double (&v)[NV > 0 ? 
     return okall;
 }
 
-// All-to-all variant of the barrier (SYNC = 1): no arrival counter, no "last CTA", no second hop.  Every CTA publishes its NV
-// block sums as tag-validated 16-byte slots {value, seq:epoch} (one release fence by thread 0 orders the CTA's writes of
-// the phase before them) and then EVERY CTA polls all the slots itself, one slot per thread, and forms the grid sum in
-// the same fixed order => identical in all CTAs and run-to-run deterministic.  Critical path per phase: one fence, one
-// store, one poll round trip and three CTA barriers, against ~8 dependent L2 round trips of the counter scheme.
-// Slots are double-buffered by epoch parity: CTA i rewrites slot[parity] two barriers later, i.e. only after every CTA
-// has published for the barrier in between, which it does after it finished reading this one.
-// For nranks > 1 CTA 0 forwards the local sums into the peers' mailboxes and the first warp of EVERY CTA polls the local
-// mailbox: the cross-rank sum needs no local re-broadcast either.
-// The sums are valid in thread 0 only (the only consumer: the scalar step); v[] holds per-thread partial sums on entry.
+// Lean variant of the barrier (SYNC = 1), shaped by tools/sync_micro.cu on the B200 (profiles/r02_sync_micro.md): a CTA
+// barrier of 1024 threads costs ~0.2 us, an L2 round trip ~0.2 us, a gpu-scope fence ~0.3 us, an arrival-counter grid barrier
+// 1.45 us, the "last CTA reduces and publishes" scheme above 2.25 us before its two serial block reductions, and an
+// all-to-all of tagged per-CTA slots 3.6 us (148 CTAs polling the same 19 lines).  So: ONE CTA barrier, then warp 0 alone
+// finishes the block sums, deposits them, arrives on the counter, polls it, and then sums the per-CTA partials ITSELF
+// (every CTA does, in the same fixed order: lane-strided, then the xor tree => identical in all CTAs, deterministic) --
+// no second hop, no broadcast slot, no further CTA barrier until the caller's own one after the scalar step.
+// For nranks > 1 CTA 0 forwards the local sums into the peers' mailboxes and warp 0 of EVERY CTA polls the local mailbox.
+// v[]: per-thread partial sums on entry; grid (and cross-rank) sums in warp 0 on return (thread 0 is the only consumer).
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.relaxed.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_relaxed_gpu_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 template <int NV>
-__device__ __forceinline__ bool pcg_sync_a2a(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
-                                             unsigned long long &epoch, unsigned long long seq, double *sh2)
+__device__ __forceinline__ bool pcg_sync_ctr(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
+                                             unsigned long long &epoch, double *sh2)
 {
     constexpr int NS = NV > 0 ? NV : 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     epoch++;
-    const unsigned long long tag = (seq << 32) | (epoch & 0xffffffffULL);
-    PcgSlot *slots = reinterpret_cast<PcgSlot *>(a.a2a) + (size_t)(epoch & 1ULL) * 3 * a.pstride;
-    double *sh = sh2 + (epoch & 1ULL) * 192;         // [2 stages][3 values][32 warps], double-buffered by parity
+    double *sh = sh2 + (epoch & 1ULL) * 96;          // [3 values][32 warps], double-buffered by parity
+    // the per-CTA partials are double-buffered by parity too: a fast CTA deposits for the NEXT barrier while a slow one is
+    // still summing this one's; the same parity is rewritten two barriers later, which nobody reaches before all have read
+    double *part = a.partials + (size_t)(epoch & 1ULL) * 3 * a.pstride;
     if (NV > 0) {
 #pragma unroll
         for (int i = 0; i < NV; i++) { const double t = warp_sum(v[i]); if (lane == 0) sh[i * 32 + wid] = t; }
     }
-    __syncthreads();                                 // the CTA's writes of this phase precede thread 0's release fence
+    __syncthreads();                                 // the CTA's writes of this phase precede lane 0's release fence
+    bool ok = true;
     if (wid == 0) {
         double t[NS];
 #pragma unroll
@@ -902,91 +1197,74 @@ __device__ __forceinline__ bool pcg_sync_a2a(const PcgArgs &a, double (&v)[NV > 
             if (NV > 0) { t[i] = lane < (int)(blockDim.x >> 5) ? sh[i * 32 + lane] : 0.0; t[i] = warp_sum(t[i]); }
         }
         if (lane == 0) {
-            __threadfence();
 #pragma unroll
-            for (int i = 0; i < NS; i++) st_slot_gpu(slots + (size_t)i * a.pstride + blockIdx.x, t[i], tag);
-        }
-    }
-    double acc[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) acc[i] = 0.0;
-    bool ok = true;
-    if ((int)threadIdx.x < (int)gridDim.x) {
-        const long long c0 = clock64();
-        for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-            double val[NS];
-            unsigned long long tg[NS];
-#pragma unroll
-            for (int i = 0; i < NS; i++) ld_slot_gpu(slots + (size_t)i * a.pstride + c, val[i], tg[i]);
-#pragma unroll
-            for (int i = 0; i < NS; i++) {
-                while (ok && tg[i] != tag) {
-                    if (clock64() - c0 > 40000000000LL) ok = false;           // ~20 s: never hang the GPU
-                    ld_slot_gpu(slots + (size_t)i * a.pstride + c, val[i], tg[i]);
-                }
-                acc[i] += val[i];
+            for (int i = 0; i < NV; i++) __stcg(part + (size_t)i * a.pstride + blockIdx.x, t[i]);
+            __threadfence();                         // release
+            red_add_relaxed_gpu_u64(a.arrive, 1ULL);
+            const unsigned long long target = (unsigned long long)gridDim.x * epoch;
+            const long long c0 = clock64();
+            while (ld_relaxed_gpu_u64(a.arrive) < target) {
+                if (clock64() - c0 > 40000000000LL) { ok = false; break; }       // ~20 s: never hang the GPU
             }
+            __threadfence();                         // acquire (+ drops this SM's stale L1 lines)
         }
-        __threadfence();                             // acquire: the other CTAs' writes of this phase are visible from here on
-    }
-    double *shb = sh + 96;
-    if (NV > 0 && wid < (int)((gridDim.x + 31) >> 5)) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) { const double t = warp_sum(acc[i]); if (lane == 0) shb[i * 32 + wid] = t; }
-    }
-    ok = __syncthreads_and(ok ? 1 : 0) != 0;
-    if (NV > 0 && wid == 0) {
-        int nw = (int)((gridDim.x + 31) >> 5);
-        if (nw > (int)(blockDim.x >> 5)) nw = (int)(blockDim.x >> 5);
-        double r[NS];
-#pragma unroll
-        for (int i = 0; i < NV; i++) { r[i] = lane < nw ? shb[i * 32 + lane] : 0.0; r[i] = warp_sum(r[i]); }
-        if (a.multi) {
-            // cross-rank sum: CTA 0 forwards, everybody polls the local mailbox, rank-order sum (bit-identical everywhere)
-            const P2pCtx *c = a.ctx;
-            const int P = c->nranks, me = c->rank;
-            if (lane < P) {
-                if (blockIdx.x == 0) {
-                    P2pMail *dst = c->mail[lane];
-#pragma unroll
-                    for (int i = 0; i < NV; i++) st_slot_sys(&dst->red[phase][me][i], r[i], ptag);
-                }
-                const P2pMail *mine = c->mail[me];
-                const long long t0 = clock64();
-#pragma unroll
-                for (int i = 0; i < NV; i++) {
-                    double val;
-                    unsigned long long tg;
-                    ld_slot_sys(&mine->red[phase][lane][i], val, tg);
-                    while (ok && tg != ptag) {
-                        if (clock64() - t0 > 20000000000LL) ok = false;          // ~10 s: dead peer
-                        ld_slot_sys(&mine->red[phase][lane][i], val, tg);
-                    }
-                    r[i] = val;
-                }
-            }
-            ok = __all_sync(0xffffffffu, ok);
+        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+        if (NV > 0) {
+            double r[NS];
 #pragma unroll
             for (int i = 0; i < NV; i++) {
                 double s0 = 0.0;
-                for (int q = 0; q < P; q++) s0 += __shfl_sync(0xffffffffu, r[i], q);
-                r[i] = s0;
+                for (int c = lane; c < (int)gridDim.x; c += 32) s0 += __ldcg(part + (size_t)i * a.pstride + c);
+                r[i] = warp_sum(s0);
             }
-        }
+            if (a.multi) {
+                // cross-rank sum: CTA 0 forwards, everybody polls the local mailbox, rank-order sum (bit-identical everywhere)
+                const P2pCtx *c = a.ctx;
+                const int P = c->nranks, me = c->rank;
+                if (lane < P) {
+                    if (blockIdx.x == 0) {
+                        P2pMail *dst = c->mail[lane];
 #pragma unroll
-        for (int i = 0; i < NV; i++) v[i] = r[i];
+                        for (int i = 0; i < NV; i++) st_slot_sys(&dst->red[phase][me][i], r[i], ptag);
+                    }
+                    const P2pMail *mine = c->mail[me];
+                    const long long t0 = clock64();
+#pragma unroll
+                    for (int i = 0; i < NV; i++) {
+                        double val;
+                        unsigned long long tg;
+                        ld_slot_sys(&mine->red[phase][lane][i], val, tg);
+                        while (ok && tg != ptag) {
+                            if (clock64() - t0 > 20000000000LL) ok = false;          // ~10 s: dead peer
+                            ld_slot_sys(&mine->red[phase][lane][i], val, tg);
+                        }
+                        r[i] = val;
+                    }
+                }
+                ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    double s0 = 0.0;
+                    for (int q = 0; q < P; q++) s0 += __shfl_sync(0xffffffffu, r[i], q);
+                    r[i] = s0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) v[i] = r[i];
+        }
     }
-    return ok;
+    if (NV == 0) __syncthreads();                    // plain barrier: nobody leaves before lane 0 has seen all arrivals
+    return ok;                                       // (NV > 0: the caller's CTA barrier after its scalar step does that)
 }
 
 // phase-end reduction + grid barrier of the persistent kernels; v[] = per-thread partial sums on entry, grid (and cross-rank)
 // sums in thread 0 on return.  SYNC 0: block sums, arrival counter, last CTA reduces and broadcasts (pcg_sync);
-// SYNC 1: all-to-all slots (pcg_sync_a2a).
+// SYNC 1: lean counter barrier, warp 0 reduces in every CTA (pcg_sync_ctr).
 template <int NV, int SYNC>
 __device__ __forceinline__ bool pcg_reduce(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
                                            unsigned long long &epoch, unsigned long long seq, double *sh, double *s_bc, double *sh2)
 {
-    if (SYNC == 1) return pcg_sync_a2a<NV>(a, v, phase, ptag, epoch, seq, sh2);
+    if (SYNC == 1) return pcg_sync_ctr<NV>(a, v, phase, ptag, epoch, sh2);
 #pragma unroll
     for (int i = 0; i < NV; i++) v[i] = block_sum(v[i], sh);
     return pcg_sync<NV>(a, v, phase, ptag, epoch, sh, s_bc);
@@ -1003,7 +1281,7 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
     __shared__ double sh[64];
     __shared__ double s_bc[4];
     __shared__ double s_push;
-    __shared__ double sh2[SYNC == 1 ? 384 : 1];
+    __shared__ double sh2[SYNC == 1 ? 192 : 1];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
     const int nloc = a.nloc;
@@ -1076,12 +1354,15 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
         };
         // ---- halo push (nranks > 1): boundary values straight into the neighbours' ghost buffers ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 1u);
-        if (a.multi) {
+        if (a.multi && a.halo_tag) {
+            for (int i = gtid; i < a.n_send; i += gthreads) st_ghost_tagged(a.send_dst_t[i], pval(a.send_idx[i]), htag);
+        } else if (a.multi) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], pval(a.send_idx[i]));
             __threadfence_system();
             __syncthreads();
             pushes++;
             if (threadIdx.x == 0) {
+                __threadfence_system();      // cumulative release: the CTA's ghost stores (ordered by the barrier) precede the ticket
                 const unsigned int t = atomicAdd(a.push_ticket, 1u);
                 s_push = (t == gridDim.x * pushes - 1u) ? 1.0 : 0.0;
             }
@@ -1119,7 +1400,11 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
                 if (a.has_off) {
                     int lo = 0, hi = 0;
                     if (r < nloc) { lo = a.off_ptr[r]; hi = a.off_ptr[r + 1]; }
-                    if (__any_sync(0xffffffffu, hi > lo)) {
+                    if (a.halo_tag) {
+                        double osum = 0.0;
+                        for (int q = lo; q < hi; q++) osum = fma(a.bval[q], ld_ghost_tagged(a.ghost_t + 2 * (size_t)a.bcol[q], htag, halo_ok), osum);
+                        sum = sum + osum;
+                    } else if (__any_sync(0xffffffffu, hi > lo)) {
                         if (!halo_ready) {       // first boundary slice of this warp in this iteration: wait for the neighbours
                             bool okw = true;
                             if (lane < a.ctx->nranks && a.ctx->recvs_from[lane])
@@ -1240,7 +1525,7 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
     __shared__ double sh[64];
     __shared__ double s_bc[4];
     __shared__ double s_push;
-    __shared__ double sh2[SYNC == 1 ? 384 : 1];
+    __shared__ double sh2[SYNC == 1 ? 192 : 1];
     __shared__ CgState ls;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
@@ -1276,12 +1561,15 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
         }
         // ---- halo push of z (nranks > 1) ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * round + 1u);
-        if (a.multi) {
+        if (a.multi && a.halo_tag) {
+            for (int i = gtid; i < a.n_send; i += gthreads) st_ghost_tagged(a.send_dst_t[i], a.z[a.send_idx[i]], htag);
+        } else if (a.multi) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], a.z[a.send_idx[i]]);
             __threadfence_system();
             __syncthreads();
             pushes++;
             if (threadIdx.x == 0) {
+                __threadfence_system();      // cumulative release (see cg_persistent_kernel)
                 const unsigned int t = atomicAdd(a.push_ticket, 1u);
                 s_push = (t == gridDim.x * pushes - 1u) ? 1.0 : 0.0;
             }
@@ -1318,7 +1606,11 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
             if (a.has_off) {
                 int lo = 0, hi = 0;
                 if (r < nloc) { lo = a.off_ptr[r]; hi = a.off_ptr[r + 1]; }
-                if (__any_sync(0xffffffffu, hi > lo)) {
+                if (a.halo_tag) {
+                    double osum = 0.0;
+                    for (int q = lo; q < hi; q++) osum = fma(a.bval[q], ld_ghost_tagged(a.ghost_t + 2 * (size_t)a.bcol[q], htag, halo_ok), osum);
+                    sum = sum + osum;
+                } else if (__any_sync(0xffffffffu, hi > lo)) {
                     if (!halo_ready) {
                         bool okw = true;
                         if (lane < a.ctx->nranks && a.ctx->recvs_from[lane])
@@ -1387,6 +1679,7 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     if (env && strcmp(env, "kernels") == 0) return PFEM_OK;
     if (h->nranks > 1 && !h->p2p) return PFEM_OK;            // the NCCL path needs host-launched collectives
     if (h->profile) return PFEM_OK;                           // per-launch SpMV timing needs separate launches
+    if (h->pc_type == PFEM_PC_BJACOBI_ILU0) return PFEM_OK;   // triangular solves run as their own (sync-free) kernels
     int coop = 0;
     PFEM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     if (!coop) return PFEM_OK;
@@ -1406,13 +1699,12 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     // 20 %, so it is off by default.
     const char *fenv = getenv("PFEM_PCG_FUSED");
     const bool fused = fenv ? (fenv[0] == '1') : false;
-    // barrier flavour: all-to-all tagged slots (one hop) where the barrier latency matters (small per-GPU blocks: the
-    // 1024 x 1 shape), arrival counter + last-CTA reduction for the 5 x 256 shape (740 CTAs polling 740 slots each is
-    // no cheaper there, and that shape is bandwidth-bound).  PFEM_PCG_SYNC=a2a|last overrides.
+    // barrier flavour: "lean" (pcg_sync_ctr: one CTA barrier, warp 0 of every CTA reduces) or "last" (pcg_sync: last CTA
+    // reduces and publishes).  PFEM_PCG_SYNC=lean|last overrides.
     const char *syenv = getenv("PFEM_PCG_SYNC");
-    const bool a2a = syenv ? (strcmp(syenv, "a2a") == 0) : (threads * minb <= 1280 && minb <= 2);
+    const bool lean = syenv ? (strcmp(syenv, "lean") == 0) : true;
 #define PCG_PICK2(T, M, S) (sr ? (const void *)cg_persistent_sr_kernel<T, M, S> : fused ? (const void *)cg_persistent_kernel<T, M, true, S> : (const void *)cg_persistent_kernel<T, M, false, S>)
-#define PCG_PICK(T, M) (a2a ? PCG_PICK2(T, M, 1) : PCG_PICK2(T, M, 0))
+#define PCG_PICK(T, M) (lean ? PCG_PICK2(T, M, 1) : PCG_PICK2(T, M, 0))
     if (threads == 256 && minb == 5) fn = PCG_PICK(256, 5);
     else if (threads == 1024 && minb == 1) fn = PCG_PICK(1024, 1);
     else if (threads == 640 && minb == 2) fn = PCG_PICK(640, 2);
@@ -1426,10 +1718,6 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     const int grid = h->sm_count * minb;
     cudaStream_t s = h->stream;
     if (!h->pcg_bcast.p) PFEM_TRY(h->pcg_bcast.alloc(16));
-    if (a2a && !h->pcg_a2a.p) {           // tags carry the solve sequence number: cleared once, never again
-        PFEM_TRY(h->pcg_a2a.alloc((size_t)2 * 3 * h->sm_count * 16 * 2));
-        PFEM_CUDA(cudaMemsetAsync(h->pcg_a2a.p, 0, h->pcg_a2a.n * sizeof(double), s));
-    }
     PFEM_CUDA(cudaMemsetAsync(h->pcg_bcast.p, 0, 16 * sizeof(double), s));
     PcgArgs a;
     memset(&a, 0, sizeof a);
@@ -1442,8 +1730,14 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
     a.x = h->x.p; a.r = h->r.p; a.z = h->z.p; a.p = h->p.p; a.w = h->w.p; a.dinv = h->dinv.p;
     a.partials = h->partials.p; a.st = h->cg.p; a.ctx = a.multi ? h->p2p_ctx.p : nullptr;
     a.send_idx = h->send_idx.p; a.send_dst = h->send_dst.p;
+    {
+        // halo flavour: tag-validated 16-byte entries (default) or values + per-neighbour flags (PFEM_PCG_HALO=flag)
+        const char *henv = getenv("PFEM_PCG_HALO");
+        a.halo_tag = (a.multi && h->send_dst_t.p && !(henv && strcmp(henv, "flag") == 0)) ? 1 : 0;
+        a.ghost_t = h->ghost_buf.p + h->ghost_tag_off;
+        a.send_dst_t = h->send_dst_t.p;
+    }
     a.bcast = h->pcg_bcast.p;
-    a.a2a = h->pcg_a2a.p;
     a.arrive = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 8);
     a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 12);
     double *svp = h->sv.p;
@@ -1539,9 +1833,18 @@ int cg_solve(pfem_solver *h)
     const char *kp = getenv("PFEM_KERNELS_P2P");
     const bool p2p = multi && h->p2p && kp && kp[0] == '1';
     const P2pCtx *ctx = p2p ? h->p2p_ctx.p : nullptr;
+    const bool ilu = h->pc_type == PFEM_PC_BJACOBI_ILU0;
+    if (ilu) {
+        // PCSetUp (numeric ILU(0) of the diagonal block), x = 0, r = b, z = M^-1 r, then (z.z, z.r)
+        cg_setup_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->row_lo, h->pc_type, h->rowptr.p, h->col.p, h->val.p, h->rhs.p, h->x.p,
+                                                  h->r.p, h->z.p, h->dinv.p, h->partials.p, pstride, h->cg.p, 0, ctx, 1);
+        h->launches++;
+        PFEM_TRY(ilu_setup(h));
+        PFEM_TRY(ilu_apply(h));
+    }
     cg_setup_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->row_lo, h->pc_type, h->rowptr.p, h->col.p, h->val.p, h->rhs.p, h->x.p,
                                               h->r.p, h->z.p, h->dinv.p, h->partials.p, pstride, h->cg.p,
-                                              p2p ? 2 : (multi ? 0 : 1), ctx);
+                                              p2p ? 2 : (multi ? 0 : 1), ctx, ilu ? 2 : 0);
     h->launches++;
     if (multi && !p2p) {
         PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 2, s));
@@ -1588,8 +1891,14 @@ int cg_solve(pfem_solver *h)
                 scalar_after_spmv_kernel<<<1, 1, 0, s>>>(h->cg.p);
                 h->launches++;
             }
+            if (ilu) {
+                cg_update_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->p.p, h->w.p, h->dinv.p, h->x.p, h->r.p, h->z.p, h->partials.p,
+                                                           pstride, h->cg.p, 0, ctx, 1);
+                h->launches++;
+                PFEM_TRY(ilu_apply(h));
+            }
             cg_update_kernel<<<gv, CG_THREADS, 0, s>>>(nloc, h->p.p, h->w.p, h->dinv.p, h->x.p, h->r.p, h->z.p, h->partials.p,
-                                                       pstride, h->cg.p, p2p ? 2 : (multi ? 0 : 1), ctx);
+                                                       pstride, h->cg.p, p2p ? 2 : (multi ? 0 : 1), ctx, ilu ? 2 : 0);
             h->launches++;
             if (multi && !p2p) {
                 PFEM_TRY(comm_allreduce_sum(h, h->cg.p->red, 2, s));

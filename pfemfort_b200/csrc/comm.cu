@@ -289,6 +289,17 @@ int comm_p2p_setup(pfem_solver *h)
             dst[i] = h->peer_ghost[q] + their_displ[q] + (i - h->send_displs[q]);
     PFEM_TRY(h->send_dst.alloc((size_t)n_send + 1));
     PFEM_CUDA(cudaMemcpy(h->send_dst.p, dst.data(), ((size_t)n_send + 1) * sizeof(double *), cudaMemcpyHostToDevice));
+    {
+        // the same for the tagged {value, tag} entries: they start ghost_tag_off doubles into the peer's buffer, and that
+        // offset depends on the peer's ghost count
+        std::vector<int> offs;
+        PFEM_TRY(comm_allgather_int(h, (int)h->ghost_tag_off, offs));
+        for (int q = 0; q < P; q++)
+            for (int i = h->send_displs[q]; i < h->send_displs[q + 1]; i++)
+                dst[i] = h->peer_ghost[q] + (size_t)offs[q] + 2 * ((size_t)their_displ[q] + (size_t)(i - h->send_displs[q]));
+        PFEM_TRY(h->send_dst_t.alloc((size_t)n_send + 1));
+        PFEM_CUDA(cudaMemcpy(h->send_dst_t.p, dst.data(), ((size_t)n_send + 1) * sizeof(double *), cudaMemcpyHostToDevice));
+    }
     P2pCtx ctx;
     memset(&ctx, 0, sizeof ctx);
     ctx.rank = me; ctx.nranks = P; ctx.seq = 0;

@@ -173,8 +173,13 @@ struct pfem_solver {
     long long nnz_off = 0;
     pfem::DevBuf<int> brow_ids, brow_ptr, bcol;   // boundary row ids (local), ptr, compact ghost index
     pfem::DevBuf<int> off_ptr;                    // [size_local+1] per-row pointer into bcol/bval (persistent CG kernel)
+    // PCBJACOBI/ILU(0): diagonal-block row ranges, factor values, inverted pivots, tagged solve vectors, row-ready epochs
+    pfem::DevBuf<int> ilu_dlo, ilu_ddiag, ilu_dhi;
+    pfem::DevBuf<double> ilu_fval, ilu_invd, ilu_y, ilu_z, ilu_ticket;
+    pfem::DevBuf<unsigned int> ilu_ready;
+    unsigned long long ilu_tickets = 0, ilu_tag = 0;
+    unsigned int ilu_epoch = 0;
     pfem::DevBuf<double> pcg_bcast;               // persistent kernel: locally broadcast reduction results + flag + push ticket
-    pfem::DevBuf<double> pcg_a2a;                 // persistent kernel, all-to-all barrier: tagged per-CTA slots
     pfem::DevBuf<double> bval;
     pfem::DevBuf<int> csr2sell;            // per CSR slot: destination (>=0 SELL entry, <0: -(offdiag entry)-1)
     std::vector<int> ghost_cols;           // global ids (sorted): PETSc garray
@@ -182,6 +187,8 @@ struct pfem_solver {
     std::vector<int> send_counts, recv_counts, send_displs, recv_displs;
     pfem::DevBuf<int> send_idx;            // local row indices to pack, grouped by destination rank
     pfem::DevBuf<double> send_buf, ghost_buf;
+    size_t ghost_tag_off = 0;                     // ghost_buf: offset (in doubles) of the tagged {value, tag} entries
+    pfem::DevBuf<double *> send_dst_t;            // per packed halo entry: address of the peer's tagged ghost entry
     pfem::DevBuf<double> x, r, z, p, w, dinv, sv;   // sv: s = A z of the single-reduction CG variant
     pfem::DevBuf<double> partials;         // [4][max_blocks]
     pfem::DevBuf<pfem::CgState> cg;

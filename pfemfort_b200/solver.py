@@ -18,7 +18,7 @@ LIBPATH = os.path.join(HERE, "libpfemb200.so")
 
 POISSON_TRIA, POISSON_TETRA, ELASTICITY_TRIA, ELASTICITY_TETRA = 0, 1, 2, 3
 KIND_DIMS = {0: (3, 1, 2), 1: (4, 1, 3), 2: (3, 2, 2), 3: (4, 3, 3)}   # npElem, ndof, ndim
-PC_NONE, PC_JACOBI = 0, 1
+PC_NONE, PC_JACOBI, PC_BJACOBI_ILU0 = 0, 1, 2     # PC_BJACOBI_ILU0: the reference's default (solverpetsc.F:206)
 
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NEG_JACOBIAN, ERR_NCCL, ERR_SIZE, ERR_NUMBERING = range(8)
 SOLVER_EMPTY, PATTERN_OK, INIT_OK, ASSEMBLY_OK, FACTORISE_OK = 1, 2, 3, 4, 5
@@ -45,6 +45,7 @@ def load_library() -> C.CDLL:
     lib.pfem_last_error.restype = C.c_char_p
     lib.pfem_solver_add_value.argtypes = [C.c_void_p, C.c_int, C.c_double]
     lib.pfem_solver_set_options.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.pfem_solver_set_options_from_file.argtypes = [C.c_void_p, C.c_char_p]
     _lib = lib
     return lib
 
@@ -187,8 +188,12 @@ class SolverB200:
         _chk(self._lib.pfem_solver_factorise_and_solve(self._h))
 
     # ---- options, mesh, pattern, batched value pass ----
-    def set_options(self, rtol=-1.0, abstol=-1.0, dtol=-1.0, max_it=-1, pc_type=PC_JACOBI):
+    def set_options(self, rtol=-1.0, abstol=-1.0, dtol=-1.0, max_it=-1, pc_type=-1):
         _chk(self._lib.pfem_solver_set_options(self._h, rtol, abstol, dtol, max_it, pc_type))
+
+    def set_options_from_file(self, path="petsc_options.dat"):
+        """PetscInitialize(..., "petsc_options.dat") + Set*FromOptions (tetrapoissonparallelimpl1.F:168, solverpetsc.F:190-210)."""
+        _chk(self._lib.pfem_solver_set_options_from_file(self._h, os.fsencode(path)))
 
     def set_mesh(self, kind, conn, coords, node_map_get_old=None):
         conn, coords = _i32(conn), _f64(coords)
@@ -250,6 +255,16 @@ class SolverB200:
         val = np.zeros(nnz.value) if values else None
         _chk(self._lib.pfem_solver_get_csr(self._h, _ptr(rowptr, C.c_int), _ptr(col, C.c_int), _ptr(val, C.c_double)))
         return rowptr, col, val
+
+    def get_ilu_factor(self):
+        """(fval on the local CSR slots, inverted pivots) of the last PC_BJACOBI_ILU0 solve."""
+        st = self.state()
+        nnz = C.c_longlong()
+        _chk(self._lib.pfem_solver_get_nnz(self._h, C.byref(nnz)))
+        fval = np.zeros(nnz.value)
+        invd = np.zeros(st["row_end"] - st["row_start"])
+        _chk(self._lib.pfem_solver_get_ilu_factor(self._h, _ptr(fval, C.c_double), _ptr(invd, C.c_double)))
+        return fval, invd
 
     def get_rhs(self):
         st = self.state()

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--mesh", default="tet10")
     ap.add_argument("--partition", default="metis")
     ap.add_argument("--out", default="")
+    ap.add_argument("--pc", default="jacobi", choices=["jacobi", "bjacobi"])
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
@@ -84,7 +85,7 @@ def main():
             idt = torch.frombuffer(bytearray(S.comm_unique_id()), dtype=torch.uint8).clone()
         dist.broadcast(idt, 0)
         s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=bytes(idt.numpy().tobytes()))
-        info = D.run_rank(s, m, num, rank=rank, rtol=1e-10)
+        info = D.run_rank(s, m, num, rank=rank, rtol=1e-10, pc_type=S.PC_BJACOBI_ILU0 if a.pc == "bjacobi" else S.PC_JACOBI)
         rp, col, val = s.get_csr()
         rhs = s.get_rhs()
         x = s.get_solution()
@@ -98,7 +99,11 @@ def main():
                                        D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, grp, gcol)
             if m.fbc_node.size:
                 O.add_force_bc(grhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, num.node_map_get_new, num.NodeDofArrayNew, num.size_global)
-            ox, oits, oreason, _ = O.cg_jacobi(grp, gcol, gval, grhs, rtol=1e-10)
+            if a.pc == "bjacobi":      # one ILU(0) block per rank, like PCBJACOBI under mpirun -np world
+                starts = [num.row_range(q)[0] for q in range(world)] + [num.size_global]
+                ox, oits, oreason, _ = O.cg_bjacobi_ilu0(grp, gcol, gval, grhs, block_start=starts, rtol=1e-10)
+            else:
+                ox, oits, oreason, _ = O.cg_jacobi(grp, gcol, gval, grhs, rtol=1e-10)
             rowlens = np.concatenate([np.diff(p[0]) for p in parts])
             result["pattern_bit_identical"] = bool(np.array_equal(rowlens, np.diff(grp)) and
                                                    np.array_equal(np.concatenate([p[1] for p in parts]), gcol))

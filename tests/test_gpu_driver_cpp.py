@@ -46,7 +46,7 @@ def _oracle_solution(m, kind, rtol):
                                             ("cookmembranetria32", "triaelasticity", S.ELASTICITY_TRIA)])
 def test_cpp_driver_single_rank(gpu, input_dir, tmp_path, name, phys, kind):
     files = _unpack(name, input_dir, str(tmp_path))
-    env = dict(os.environ, PFEM_KSP_RTOL="1e-10")
+    env = dict(os.environ, PFEM_KSP_RTOL="1e-10", PFEM_PC_TYPE="jacobi")
     r = subprocess.run([DRIVER, phys] + files, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     m = M.read_mesh(os.path.join(input_dir, name))
@@ -66,7 +66,7 @@ def test_cpp_driver_two_ranks(gpu, input_dir, tmp_path):
     if S.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     files = _unpack("tet10", input_dir, str(tmp_path))
-    env = dict(os.environ, PFEM_KSP_RTOL="1e-10", PFEM_NCCL_ID_FILE=os.path.join(str(tmp_path), "nccl.id"))
+    env = dict(os.environ, PFEM_KSP_RTOL="1e-10", PFEM_PC_TYPE="jacobi", PFEM_NCCL_ID_FILE=os.path.join(str(tmp_path), "nccl.id"))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29641", DRIVER, "tetrapoisson"] + files
     r = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
@@ -78,3 +78,27 @@ def test_cpp_driver_two_ranks(gpu, input_dir, tmp_path):
     u[t[:, 1].astype(int) - 1] = t[:, 2]
     free = t[:, 1].astype(int) - 1
     assert np.abs(u[free] - (m.coords[:, free] ** 2).sum(0)).max() < 2e-7
+
+
+def test_cpp_driver_reference_defaults_and_options_file(gpu, input_dir, tmp_path):
+    """No options at all: the reference's coded defaults, CG + PCBJACOBI/ILU(0) at rtol 1e-5 (solverpetsc.F:187,206);
+    with a petsc_options.dat in the working directory (PetscInitialize, tetrapoissonparallelimpl1.F:168): its options."""
+    files = _unpack("tet10", input_dir, str(tmp_path))
+    m = M.read_mesh(os.path.join(input_dir, "tet10"))
+    num = D.number(m, S.POISSON_TETRA)
+    rp, col = O.pattern(num.elemDof, num.size_global)
+    val, rhs, _ = O.assemble(S.POISSON_TETRA, num.conn_new, m.coords, None, num.elemDof, num.solnApplied,
+                             D.DEFAULT_ELEMDATA[S.POISSON_TETRA], D.DEFAULT_TIMEDATA, rp, col)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("PFEM_")}
+    r = subprocess.run([DRIVER, "tetrapoisson"] + files, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ox, oits, _, _ = O.cg_bjacobi_ilu0(rp, col, val, rhs, rtol=1e-5)
+    assert f"Convergence in {oits} iterations." in r.stdout, r.stdout
+    t = np.loadtxt(os.path.join(str(tmp_path), "temp.dat"))
+    assert np.abs(t[:, 2] - ox).max() <= 1e-6 * np.abs(ox).max()
+    with open(os.path.join(str(tmp_path), "petsc_options.dat"), "w") as f:
+        f.write("-ksp_type cg\n-pc_type jacobi\n-ksp_rtol 1e-10\n")
+    r = subprocess.run([DRIVER, "tetrapoisson"] + files, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ox, oits, _, _ = O.cg_jacobi(rp, col, val, rhs, rtol=1e-10)
+    assert any(f"Convergence in {k} iterations." in r.stdout for k in (oits - 1, oits, oits + 1)), r.stdout

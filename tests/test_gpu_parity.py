@@ -270,8 +270,8 @@ def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch):
 
 # (PFEM_CG, PFEM_CG_SR, PFEM_PCG_FUSED, PFEM_PCG_SYNC, PFEM_PCG_CFG); entry 1 is the launch-per-phase reference point
 CG_VARIANTS = (("persistent", "0", "0", "", ""), ("kernels", "0", "0", "", ""), ("persistent", "1", "0", "", ""),
-               ("persistent", "0", "1", "", ""), ("persistent", "0", "0", "last", "1024x1"), ("persistent", "0", "0", "a2a", "1024x1"),
-               ("persistent", "0", "0", "a2a", "256x5"), ("persistent", "1", "0", "a2a", "512x2"), ("persistent", "0", "1", "last", "256x5"))
+               ("persistent", "0", "1", "", ""), ("persistent", "0", "0", "last", "1024x1"), ("persistent", "0", "0", "lean", "1024x1"),
+               ("persistent", "0", "0", "lean", "256x5"), ("persistent", "1", "0", "lean", "512x2"), ("persistent", "0", "1", "last", "256x5"))
 
 
 def _set_cg_variant(monkeypatch, v):
@@ -459,4 +459,55 @@ def test_petscsolver_assemble_mirrors(gpu, input_dir):
     ref_rhs[5] += 1.5
     assert np.array_equal(s.get_rhs(), ref_rhs)
     assert s.launch_count() > 0 and s.time_spmv(3) > 0.0
+    s.free()
+
+
+# ---- the reference's default preconditioner: PCBJACOBI / ILU(0) (solverpetsc.F:206) ----------------------------------
+
+@pytest.mark.parametrize("name", ["tet10", "tria20x20", "beam3Dtet6366", "cookmembranetria32"])
+def test_bjacobi_ilu0_cg_matches_oracle(gpu, input_dir, name):
+    """CG + block-Jacobi/ILU(0) on one rank (= ILU(0) of the whole matrix): the factor and the inverted pivots are
+    bit-identical to the sequential oracle (the sync-free kernels keep the sequential operation order), iteration
+    counts and reason equal the oracle's, solutions agree to the solver tolerance."""
+    m, kind = _load(name, input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    for rtol in (1e-5, 1e-10):
+        info = D.run_rank(s, m, num, rtol=rtol, pc_type=S.PC_BJACOBI_ILU0)
+        rp, col, val = s.get_csr()
+        rhs = s.get_rhs()
+        ofv, oinv, rc = O.ilu0_factor(rp, col, val)
+        assert rc == 0
+        fv, inv = s.get_ilu_factor()
+        assert np.array_equal(fv, ofv) and np.array_equal(inv, oinv), "ILU(0) factor differs from the oracle"
+        ox, oits, oreason, _ = O.cg_bjacobi_ilu0(rp, col, val, rhs, rtol=rtol)
+        assert info["reason"] == oreason == 2
+        assert abs(info["its"] - oits) <= max(1, ITS_TOL * oits), (info["its"], oits)
+        x = s.get_solution()
+        assert np.abs(x - ox).max() <= 10 * rtol * np.abs(ox).max()
+        info2 = D.run_rank(s, m, num, rtol=rtol, pc_type=S.PC_BJACOBI_ILU0)
+        assert (info2["its"], info2["reason"]) == (info["its"], info["reason"]) and np.array_equal(s.get_solution(), x), "determinism"
+    s.free()
+
+
+def test_default_pc_is_the_references_and_options_file(gpu, input_dir, tmp_path):
+    """pfem_solver_initialise leaves the reference's coded defaults (CG + PCBJACOBI/ILU(0), rtol 1e-5); an options file
+    in PETSc's syntax overrides them; unsupported types are refused."""
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    info = D.run_rank(s, m, num, rtol=-1.0, pc_type=-1)            # nothing overridden
+    rp, col, val = s.get_csr()
+    ox, oits, oreason, _ = O.cg_bjacobi_ilu0(rp, col, val, s.get_rhs(), rtol=1e-5)
+    assert (info["its"], info["reason"]) == (oits, oreason)
+    opt = tmp_path / "petsc_options.dat"
+    opt.write_text("-ksp_type cg\n-pc_type jacobi   # north-star run\n-ksp_rtol 1e-10\n-log_view\n")
+    s.set_options_from_file(str(opt))
+    s.factoriseAndSolve()                                          # same assembled system, new options
+    ox, oits, oreason, _ = O.cg_jacobi(rp, col, val, s.get_rhs(), rtol=1e-10)
+    assert abs(s.info()["its"] - oits) <= 1 and s.info()["reason"] == oreason
+    opt.write_text("-pc_type gamg\n")
+    with pytest.raises(S.PfemError):
+        s.set_options_from_file(str(opt))
+    s.set_options_from_file(str(tmp_path / "absent.dat"))          # no file: defaults stay
     s.free()

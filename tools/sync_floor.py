@@ -12,7 +12,7 @@ from pfemfort_b200 import driver as D, mesh as M, solver as S  # noqa: E402
 for cells in [int(a) for a in sys.argv[1:]] or [16, 32]:
     m = M.gen_tetra(-1, 1, cells, -1, 1, cells, -1, 1, cells)
     num = D.number(m, S.POISSON_TETRA)
-    for sync in ("last", "a2a"):                      # barrier flavour of the persistent kernel (cg.cu: pcg_sync / pcg_sync_a2a)
+    for sync in ("last", "lean"):                      # barrier flavour of the persistent kernel (cg.cu: pcg_sync / pcg_sync_ctr)
         os.environ["PFEM_PCG_SYNC"] = sync
         s = S.SolverB200(0)
         best = None
