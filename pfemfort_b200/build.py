@@ -49,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                                                                os.path.join(HERE, "..", "drivers", "pfem_driver.cpp"),
                                                                os.path.abspath(__file__)]
     stamp = os.path.join(OBJDIR, "stamp")
-    dig = _digest(deps)
+    extra = os.environ.get("PFEM_EXTRA_NVCC", "").split()      # e.g. -DPFEM_PCG_TRACE (tools/pcg_trace.py); part of the stamp
+    dig = _digest(deps) + "|" + " ".join(extra)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
@@ -58,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmds = []
     for src in SOURCES:
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if src in NO_FMA:
             cmd.insert(1, "-fmad=false")
         if src in OPENMP:

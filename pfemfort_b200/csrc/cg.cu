@@ -26,6 +26,15 @@ namespace pfem {
 
 static constexpr int CG_THREADS = 256;
 
+// Build with -DPFEM_PCG_TRACE to time-stamp (clock64, CTA 0 / thread 0) the stages of the persistent kernel's last
+// iteration; read back with pfem_debug_pcg_trace (tools/pcg_trace.py).  Compiled out by default.
+#ifdef PFEM_PCG_TRACE
+__device__ long long g_pcg_trace[64];
+#define PCG_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_pcg_trace[(k)] = clock64(); } while (0)
+#else
+#define PCG_T(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -458,7 +467,7 @@ int build_solver_structures(pfem_solver *h)
     h->ghost_tag_off = ((size_t)h->n_ghost + 2) & ~(size_t)1;
     PFEM_TRY(h->ghost_buf.alloc(h->ghost_tag_off + 2 * ((size_t)h->n_ghost + 1)));
     PFEM_CUDA(cudaMemsetAsync(h->ghost_buf.p, 0, h->ghost_buf.n * sizeof(double), h->stream));
-    PFEM_TRY(h->partials.alloc((size_t)8 * h->sm_count * 16));     // pcg_sync_ctr: [2 epoch parities][3 values][pstride]
+    PFEM_TRY(h->partials.alloc((size_t)4 * h->sm_count * 16));
     if (!h->cg.p) {
         PFEM_TRY(h->cg.alloc(1));
         PFEM_CUDA(cudaMemsetAsync(h->cg.p, 0, sizeof(CgState), s));
@@ -1052,7 +1061,9 @@ struct PcgArgs {
     double *bcast;                         // 4 PcgSlot {value, epoch}: [0..2] reduction results, [3] ok flag / release
     unsigned long long *arrive;            // monotonically increasing CTA arrival counter of the barriers
     unsigned int *push_ticket;             // monotonically increasing CTA arrival counter of the halo pushes
+    double *parts;                         // pcg_sync_ctr: replicated per-CTA partial records [2][PCG_REPL][pstride][4]
 };
+static constexpr int PCG_REPL = 16;
 
 __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
 {
@@ -1174,7 +1185,7 @@ __device__ __forceinline__ void red_add_relaxed_gpu_u64(unsigned long long *p, u
 
 template <int NV>
 __device__ __forceinline__ bool pcg_sync_ctr(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
-                                             unsigned long long &epoch, double *sh2)
+                                             unsigned long long &epoch, double *sh2, int tb = 0)
 {
     constexpr int NS = NV > 0 ? NV : 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1182,12 +1193,16 @@ __device__ __forceinline__ bool pcg_sync_ctr(const PcgArgs &a, double (&v)[NV > 
     double *sh = sh2 + (epoch & 1ULL) * 96;          // [3 values][32 warps], double-buffered by parity
     // the per-CTA partials are double-buffered by parity too: a fast CTA deposits for the NEXT barrier while a slow one is
     // still summing this one's; the same parity is rewritten two barriers later, which nobody reaches before all have read
-    double *part = a.partials + (size_t)(epoch & 1ULL) * 3 * a.pstride;
+    // Layout [parity][replica][CTA] of 32-byte records {v0, v1, v2, -}: every CTA deposits PCG_REPL copies (16 lanes, one store
+    // each) and CTA c sums replica c % PCG_REPL, so a 128-byte line has ~9 readers instead of 148 (the trace showed the
+    // all-CTAs-read-the-same-19-lines sum costing 1500-5600 cycles), and all NV values of a CTA come in one record.
+    double *part = a.parts + (size_t)(epoch & 1ULL) * PCG_REPL * a.pstride * 4;
     if (NV > 0) {
 #pragma unroll
         for (int i = 0; i < NV; i++) { const double t = warp_sum(v[i]); if (lane == 0) sh[i * 32 + wid] = t; }
     }
     __syncthreads();                                 // the CTA's writes of this phase precede lane 0's release fence
+    PCG_T(tb + 1);
     bool ok = true;
     if (wid == 0) {
         double t[NS];
@@ -1196,26 +1211,40 @@ __device__ __forceinline__ bool pcg_sync_ctr(const PcgArgs &a, double (&v)[NV > 
             t[i] = 0.0;
             if (NV > 0) { t[i] = lane < (int)(blockDim.x >> 5) ? sh[i * 32 + lane] : 0.0; t[i] = warp_sum(t[i]); }
         }
+        if (NV > 0 && lane < PCG_REPL) {
+            double2 *rec = reinterpret_cast<double2 *>(part + ((size_t)lane * a.pstride + blockIdx.x) * 4);
+            __stcg(rec, make_double2(t[0], NV > 1 ? t[1] : 0.0));
+            if (NV > 2) __stcg(rec + 1, make_double2(t[2], 0.0));
+        }
+        __syncwarp();
         if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) __stcg(part + (size_t)i * a.pstride + blockIdx.x, t[i]);
-            __threadfence();                         // release
+            __threadfence();                         // release (cumulative over the warp's deposits and the CTA's phase writes)
+            PCG_T(tb + 2);
             red_add_relaxed_gpu_u64(a.arrive, 1ULL);
             const unsigned long long target = (unsigned long long)gridDim.x * epoch;
             const long long c0 = clock64();
             while (ld_relaxed_gpu_u64(a.arrive) < target) {
                 if (clock64() - c0 > 40000000000LL) { ok = false; break; }       // ~20 s: never hang the GPU
             }
+            PCG_T(tb + 3);
             __threadfence();                         // acquire (+ drops this SM's stale L1 lines)
+            PCG_T(tb + 4);
         }
         ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
         if (NV > 0) {
             double r[NS];
-#pragma unroll
-            for (int i = 0; i < NV; i++) {
-                double s0 = 0.0;
-                for (int c = lane; c < (int)gridDim.x; c += 32) s0 += __ldcg(part + (size_t)i * a.pstride + c);
-                r[i] = warp_sum(s0);
+            {
+                const double *rep = part + (size_t)(blockIdx.x % PCG_REPL) * a.pstride * 4;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                for (int c = lane; c < (int)gridDim.x; c += 32) {
+                    const double2 u = __ldcg(reinterpret_cast<const double2 *>(rep + (size_t)c * 4));
+                    s0 += u.x;
+                    if (NV > 1) s1 += u.y;
+                    if (NV > 2) s2 += __ldcg(rep + (size_t)c * 4 + 2);
+                }
+                r[0] = warp_sum(s0);
+                if (NV > 1) r[NV > 1 ? 1 : 0] = warp_sum(s1);
+                if (NV > 2) r[NV > 2 ? 2 : 0] = warp_sum(s2);
             }
             if (a.multi) {
                 // cross-rank sum: CTA 0 forwards, everybody polls the local mailbox, rank-order sum (bit-identical everywhere)
@@ -1253,6 +1282,7 @@ __device__ __forceinline__ bool pcg_sync_ctr(const PcgArgs &a, double (&v)[NV > 
             for (int i = 0; i < NV; i++) v[i] = r[i];
         }
     }
+    PCG_T(tb + 5);
     if (NV == 0) __syncthreads();                    // plain barrier: nobody leaves before lane 0 has seen all arrivals
     return ok;                                       // (NV > 0: the caller's CTA barrier after its scalar step does that)
 }
@@ -1262,9 +1292,10 @@ __device__ __forceinline__ bool pcg_sync_ctr(const PcgArgs &a, double (&v)[NV > 
 // SYNC 1: lean counter barrier, warp 0 reduces in every CTA (pcg_sync_ctr).
 template <int NV, int SYNC>
 __device__ __forceinline__ bool pcg_reduce(const PcgArgs &a, double (&v)[NV > 0 ? NV : 1], int phase, unsigned long long ptag,
-                                           unsigned long long &epoch, unsigned long long seq, double *sh, double *s_bc, double *sh2)
+                                           unsigned long long &epoch, unsigned long long seq, double *sh, double *s_bc, double *sh2,
+                                           int tb = 0)
 {
-    if (SYNC == 1) return pcg_sync_ctr<NV>(a, v, phase, ptag, epoch, sh2);
+    if (SYNC == 1) return pcg_sync_ctr<NV>(a, v, phase, ptag, epoch, sh2, tb);
 #pragma unroll
     for (int i = 0; i < NV; i++) v[i] = block_sum(v[i], sh);
     return pcg_sync<NV>(a, v, phase, ptag, epoch, sh, s_bc);
@@ -1325,6 +1356,7 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
     }
 
     while (ls.reason == 0) {
+        PCG_T(0);
         // ---- direction: p = z + b p ----
         const bool first = ls.iter == 0;
         const double bdir = ls.b;
@@ -1345,7 +1377,9 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
             }
             if ((nloc & 1) && gtid == 0) a.p[nloc - 1] = first ? a.z[nloc - 1] : a.z[nloc - 1] + b * a.p[nloc - 1];
             double none[1] = {0.0};
-            pcg_reduce<0, SYNC>(a, none, 0, 0ULL, epoch, ls.seq, sh, s_bc, sh2);
+            PCG_T(1);
+            pcg_reduce<0, SYNC>(a, none, 0, 0ULL, epoch, ls.seq, sh, s_bc, sh2, 1);
+            PCG_T(7);
         }
         auto pval = [&](int c) -> double {     // entry c of the current direction
             if (!FUSED) return a.p[c];
@@ -1426,14 +1460,17 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
             }
             double v[1] = {pw};
             if (!halo_ok) v[0] = __longlong_as_double(0x7ff8000000000000LL);
+            PCG_T(10);
             const bool ok = pcg_reduce<1, SYNC>(a, v, 0, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 2u), epoch,
-                                                ls.seq, sh, s_bc, sh2);
+                                                ls.seq, sh, s_bc, sh2, 10);
             pw = v[0];
             if (threadIdx.x == 0) {
                 step_after_spmv(&ls, pw);
                 if (!ok || pw != pw) ls.reason = -101;
             }
+            PCG_T(16);
             __syncthreads();
+            PCG_T(17);
         }
         if (ls.reason != 0) break;
         // ---- update: x += a p, r -= a w, z = M^-1 r, (z.z, z.r) ----
@@ -1461,14 +1498,17 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
                 zz = fma(zv, zv, zz); zr = fma(zv, rv, zr);
             }
             double v[2] = {zz, zr};
+            PCG_T(20);
             const bool ok = pcg_reduce<2, SYNC>(a, v, 1, (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 3u), epoch,
-                                                ls.seq, sh, s_bc, sh2);
+                                                ls.seq, sh, s_bc, sh2, 20);
             zz = v[0]; zr = v[1];
             if (threadIdx.x == 0) {
                 step_after_update(&ls, zz, zr);
                 if (!ok) ls.reason = -101;
             }
+            PCG_T(26);
             __syncthreads();
+            PCG_T(27);
         }
     }
     if (gtid == 0) {
@@ -1738,6 +1778,8 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
         a.send_dst_t = h->send_dst_t.p;
     }
     a.bcast = h->pcg_bcast.p;
+    if (!h->pcg_parts.p) PFEM_TRY(h->pcg_parts.alloc((size_t)2 * PCG_REPL * a.pstride * 4));
+    a.parts = h->pcg_parts.p;
     a.arrive = reinterpret_cast<unsigned long long *>(h->pcg_bcast.p + 8);
     a.push_ticket = reinterpret_cast<unsigned int *>(h->pcg_bcast.p + 12);
     double *svp = h->sv.p;
@@ -1946,3 +1988,13 @@ int time_spmv(pfem_solver *h, int reps, double *seconds)
 }
 
 }  // namespace pfem
+
+extern "C" int pfem_debug_pcg_trace(long long *out64)
+{
+#ifdef PFEM_PCG_TRACE
+    return cudaMemcpyFromSymbol(out64, pfem::g_pcg_trace, 64 * sizeof(long long)) == cudaSuccess ? 0 : PFEM_ERR_CUDA;
+#else
+    (void)out64;
+    return PFEM_ERR_STATE;      // not a trace build
+#endif
+}

@@ -179,6 +179,7 @@ struct pfem_solver {
     pfem::DevBuf<unsigned int> ilu_ready;
     unsigned long long ilu_tickets = 0, ilu_tag = 0;
     unsigned int ilu_epoch = 0;
+    pfem::DevBuf<double> pcg_parts;               // persistent kernel, lean barrier: replicated per-CTA partial records
     pfem::DevBuf<double> pcg_bcast;               // persistent kernel: locally broadcast reduction results + flag + push ticket
     pfem::DevBuf<double> bval;
     pfem::DevBuf<int> csr2sell;            // per CSR slot: destination (>=0 SELL entry, <0: -(offdiag entry)-1)

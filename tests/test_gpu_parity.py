@@ -253,8 +253,9 @@ def test_generated_tria_and_tet(gpu, n):
     s.free()
 
 
-def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch):
-    """Rows wider than 254 entries fall back to the binary-search kernel; force it and compare bit for bit."""
+def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch, asm_mode):
+    """Rows wider than 254 entries fall back to the binary-search kernel; force it and compare bit for bit (under
+    PFEM_ASM=fast the fallback keeps the reference-order operators: 1e-12 contract between the two)."""
     for name in ("tet10", "beam3Dtet6366"):
         m, kind = _load(name, input_dir)
         num = D.number(m, kind)
@@ -265,7 +266,12 @@ def test_generic_assembly_kernel_matches_streamed(gpu, input_dir, monkeypatch):
             D.run_rank(s, m, num, do_solve=False)
             out.append((s.get_csr()[2], s.get_rhs()))
             s.free()
-        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        if asm_mode == "rows":
+            assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        else:
+            scale = np.abs(out[1][0]).max()
+            assert np.abs(out[0][0] - out[1][0]).max() <= REL_TOL_VALUES * scale
+            assert np.abs(out[0][1] - out[1][1]).max() <= REL_TOL_VALUES * max(np.abs(out[1][1]).max(), 1e-300)
 
 
 # (PFEM_CG, PFEM_CG_SR, PFEM_PCG_FUSED, PFEM_PCG_SYNC, PFEM_PCG_CFG); entry 1 is the launch-per-phase reference point
