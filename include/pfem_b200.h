@@ -213,6 +213,46 @@ int pfem_solver_get_profile(pfem_solver_t *h, double *spmv_seconds_total, long l
 /* PetscSolver%printInfo, solverpetsc.F:286-320 */
 int pfem_solver_print_info(pfem_solver_t *h);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Explicit dynamics: the matrix-free element residual / lumped-mass routines and the
+ * central-difference time loop of the *elasticityexplicit drivers.  No matrix, no solver object.
+ * Single-element entry points mirror the Fortran routines argument for argument (status PFEM_ERR_NEG_JACOBIAN where
+ * they STOP):
+ *   ResidualElasticityLinearTria   elementutilitieselasticity2D.F:158-275  (plane strain; Flocal[6])
+ *   MassMatrixLinearTria           elementutilitieselasticity2D.F:283-362  (Mlocal[6], row sums = lumped mass)
+ *   ResidualElasticityLinearTetra  elementutilitieselasticity3D.F:575-723  (Flocal[12]; ETYPE 4 / one Gauss point intent)
+ *   MassMatrixLinearTetra          elementutilitieselasticity3D.F:401-482  (Mlocal[12])
+ * elemData = (E, nu, density, bx, by[, bz]); timeData and the velocity argument are accepted and, like in the reference,
+ * unused. */
+int pfem_residual_elasticity_linear_tria(const double *x, const double *y, const double *elemData, const double *timeData,
+                                         const double *dispC, const double *veloC, double *Flocal);
+int pfem_mass_matrix_linear_tria(const double *x, const double *y, const double *elemData, double *Mlocal);
+int pfem_residual_elasticity_linear_tetra(const double *x, const double *y, const double *z, const double *elemData,
+                                          const double *timeData, const double *valC, const double *valDotC, double *Flocal);
+int pfem_mass_matrix_linear_tetra(const double *x, const double *y, const double *z, const double *elemData, double *Mlocal);
+
+/* Batched time loop (one call replaces the element loops of triaelasticityexplicit.F:881-921 and :972-1121).
+ * Arrays as in the driver: conn SoA [npElem][nElem] 1-based, coords SoA [ndim][nNode]; displacement / velocity /
+ * acceleration / mass are indexed by node slot (node-1)*ndof + dof like the driver's plain arrays; assyForSoln lists the
+ * 1-based slots of the free dofs (:722-734), all other dofs keep their value (the reference never touches them).
+ * One process, one GPU (the explicit drivers loop over ALL elements on every rank). */
+typedef struct pfem_explicit pfem_explicit_t;
+int pfem_explicit_create(pfem_explicit_t **ex, int device);
+int pfem_explicit_free(pfem_explicit_t *ex);
+int pfem_explicit_set_mesh(pfem_explicit_t *ex, int kind /* PFEM_ELASTICITY_TRIA | PFEM_ELASTICITY_TETRA */, int nElem, const int *conn,
+                           int nNode, const double *coords);
+int pfem_explicit_set_free_dofs(pfem_explicit_t *ex, int size_global, const int *assyForSoln);
+/* globalM: triaelasticityexplicit.F:881-921 */
+int pfem_explicit_lumped_mass(pfem_explicit_t *ex, const double *elemData);
+/* nsteps passes of the time loop body (:972-1121) with constant elemData (the driver's load switch at timeNow <= 0.1 is
+   host logic: call once per load phase) */
+int pfem_explicit_advance(pfem_explicit_t *ex, int nsteps, double dt, const double *elemData, const double *timeData);
+/* any output may be NULL; disp = current displacement (= dispPrev of the next step), dispPrev2 = the one before */
+int pfem_explicit_get_state(pfem_explicit_t *ex, double *disp, double *dispPrev2, double *velo, double *acce, double *mass);
+/* restart from a saved (disp, dispPrev2) pair: resume is bit-identical to an uninterrupted run */
+int pfem_explicit_set_state(pfem_explicit_t *ex, const double *disp, const double *dispPrev2);
+int pfem_explicit_get_info(pfem_explicit_t *ex, long long *steps, long long *launches, double *t_advance);
+
 #ifdef __cplusplus
 }
 #endif

@@ -825,6 +825,232 @@ ORC_API int orc_cg_bjacobi_ilu0(int N, const int *rowptr, const int *col, const 
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* Explicit dynamics: matrix-free element residual, lumped mass, central-difference   */
+/* time loop of triaelasticityexplicit.F.  Single-precision literals (1.0/3.0, 1.0/6.0) reproduced.         */
+/* 3-D routines under the documented intent of SURVEY.md 8c (ETYPE 4, one Gauss point).                     */
+/* kind: 2 = tria (plane strain), 3 = tet.  Return 1 for a negative Jacobian (the reference STOPs).          */
+/* ------------------------------------------------------------------------- */
+
+/* elementutilitieselasticity2D.F:158-275 ResidualElasticityLinearTria */
+ORC_API int orc_residual_elasticity_tria(const double *x, const double *y, const double *elemData, const double *timeData,
+                                         const double *dispC, const double *veloC, double *Flocal)
+{
+    (void)timeData; (void)veloC;                       /* af, timefact and veloC are read but unused (:213-214) */
+    double E = elemData[0], nu = elemData[1], dens = elemData[2], thick = 1.0;    /* :188-194 */
+    double bforce[2] = {elemData[3], elemData[4]};
+    double Dmat[3][3];
+    double b1 = E / ((1.0 + nu) * (1.0 - 2.0 * nu));   /* plane strain, :203-206 */
+    Dmat[0][0] = b1 * (1.0 - nu); Dmat[0][1] = b1 * nu;         Dmat[0][2] = 0.0;
+    Dmat[1][0] = b1 * nu;         Dmat[1][1] = b1 * (1.0 - nu); Dmat[1][2] = 0.0;
+    Dmat[2][0] = 0.0;             Dmat[2][1] = 0.0;             Dmat[2][2] = b1 * (1.0 - 2.0 * nu) * 0.5;
+    double param[2] = {(double)(1.0f / 3.0f), (double)(1.0f / 3.0f)}, gw = 0.5;   /* :219 */
+    double N[3], dNdx[3], dNdy[3], Jac;
+    for (int i = 0; i < 6; i++) Flocal[i] = 0.0;
+    basis2d_tria(param, x, y, N, dNdx, dNdy, &Jac);
+    if (Jac < 0.0) return 1;                           /* :235-237 */
+    double dvol = gw * (Jac * thick);                  /* :239 */
+    double grad[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int ii = 0; ii < 3; ii++) {                   /* :244-254 */
+        double c1 = dispC[2 * ii], c2 = dispC[2 * ii + 1];
+        grad[0][0] = grad[0][0] + c1 * dNdx[ii];
+        grad[0][1] = grad[0][1] + c1 * dNdy[ii];
+        grad[1][0] = grad[1][0] + c2 * dNdx[ii];
+        grad[1][1] = grad[1][1] + c2 * dNdy[ii];
+    }
+    double strain[3] = {grad[0][0], grad[1][1], 0.5 * (grad[0][1] + grad[1][0])}, stress[3];   /* :257-259 */
+    for (int i = 0; i < 3; i++) {                      /* MATMUL(Dmat, strain) :261 */
+        double sacc = 0.0;
+        for (int j = 0; j < 3; j++) sacc = sacc + Dmat[i][j] * strain[j];
+        stress[i] = sacc;
+    }
+    for (int ii = 0; ii < 3; ii++) {                   /* :264-274 */
+        double c1 = dvol * dNdx[ii], c2 = dvol * dNdy[ii], c4 = (dens * dvol) * N[ii];
+        Flocal[2 * ii]     = ((Flocal[2 * ii]     + c4 * bforce[0]) - c1 * stress[0]) - c2 * stress[2];
+        Flocal[2 * ii + 1] = ((Flocal[2 * ii + 1] + c4 * bforce[1]) - c1 * stress[2]) - c2 * stress[1];
+    }
+    return 0;
+}
+
+/* elementutilitieselasticity2D.F:283-362 MassMatrixLinearTria: row sums of the consistent mass = lumped mass */
+ORC_API int orc_mass_matrix_tria(const double *x, const double *y, const double *elemData, double *Mlocal)
+{
+    double dens = elemData[2];
+    double param[2] = {(double)(1.0f / 3.0f), (double)(1.0f / 3.0f)}, gw = 0.5;
+    double N[3], dNdx[3], dNdy[3], Jac, K[6][6];
+    memset(K, 0, sizeof K);
+    basis2d_tria(param, x, y, N, dNdx, dNdy, &Jac);
+    if (Jac < 0.0) return 1;
+    double dvol = gw * Jac;                            /* :325 */
+    for (int ii = 0; ii < 3; ii++) {
+        double b4 = (dens * dvol) * N[ii];             /* :333 */
+        for (int jj = 0; jj < 3; jj++) {
+            double fact = b4 * N[jj];
+            K[2 * ii][2 * jj] = K[2 * ii][2 * jj] + fact;
+            K[2 * ii + 1][2 * jj + 1] = K[2 * ii + 1][2 * jj + 1] + fact;
+        }
+    }
+    for (int ii = 0; ii < 6; ii++) {                   /* :352-359 */
+        double fact = 0.0;
+        for (int jj = 0; jj < 6; jj++) fact = fact + K[ii][jj];
+        Mlocal[ii] = fact;
+    }
+    return 0;
+}
+
+/* elementutilitieselasticity3D.F:575-723 ResidualElasticityLinearTetra (ETYPE 4 intent) */
+ORC_API int orc_residual_elasticity_tet(const double *x, const double *y, const double *z, const double *elemData,
+                                        const double *timeData, const double *valC, const double *valDotC, double *Flocal)
+{
+    (void)timeData; (void)valDotC;
+    double E = elemData[0], nu = elemData[1];
+    double bforce[3] = {elemData[3], elemData[4], elemData[5]};
+    double b1 = E / ((1.0 + nu) * (1.0 - 2.0 * nu)), b2 = (1.0 - 2.0 * nu) / 2.0;      /* :617-618 */
+    double Dmat[6][6];
+    memset(Dmat, 0, sizeof Dmat);
+    Dmat[0][0] = b1 * (1.0 - nu); Dmat[0][1] = b1 * nu;         Dmat[0][2] = b1 * nu;
+    Dmat[1][0] = b1 * nu;         Dmat[1][1] = b1 * (1.0 - nu); Dmat[1][2] = b1 * nu;
+    Dmat[2][0] = b1 * nu;         Dmat[2][1] = b1 * nu;         Dmat[2][2] = b1 * (1.0 - nu);
+    Dmat[3][3] = b1 * b2; Dmat[4][4] = b1 * b2; Dmat[5][5] = b1 * b2;
+    double param[3] = {0.25, 0.25, 0.25}, gw = (double)(1.0f / 6.0f);                  /* :637-638 */
+    double N[4], dNdx[4], dNdy[4], dNdz[4], Jac;
+    for (int i = 0; i < 12; i++) Flocal[i] = 0.0;
+    basis3d_tet(param, x, y, z, N, dNdx, dNdy, dNdz, &Jac);
+    if (Jac < 0.0) return 1;
+    double dvol = gw * Jac;                            /* :657 */
+    double grad[3][3];
+    memset(grad, 0, sizeof grad);
+    for (int ii = 0; ii < 4; ii++) {                   /* :661-679 */
+        double c[3] = {valC[3 * ii], valC[3 * ii + 1], valC[3 * ii + 2]};
+        for (int r = 0; r < 3; r++) {
+            grad[r][0] = grad[r][0] + c[r] * dNdx[ii];
+            grad[r][1] = grad[r][1] + c[r] * dNdy[ii];
+            grad[r][2] = grad[r][2] + c[r] * dNdz[ii];
+        }
+    }
+    double strain[6] = {grad[0][0], grad[1][1], grad[2][2], 0.5 * (grad[0][1] + grad[1][0]), 0.5 * (grad[1][2] + grad[2][1]),
+                        0.5 * (grad[0][2] + grad[2][0])}, stress[6];                   /* :682-687 */
+    for (int i = 0; i < 6; i++) {                      /* MATMUL(Dmat, strain) :689 */
+        double sacc = 0.0;
+        for (int j = 0; j < 6; j++) sacc = sacc + Dmat[i][j] * strain[j];
+        stress[i] = sacc;
+    }
+    for (int ii = 0; ii < 4; ii++) {                   /* :705-721 */
+        double c1 = dvol * dNdx[ii], c2 = dvol * dNdy[ii], c3 = dvol * dNdz[ii], c4 = dvol * N[ii];
+        double *F = Flocal + 3 * ii;
+        F[0] = F[0] + c4 * bforce[0];
+        F[1] = F[1] + c4 * bforce[1];
+        F[2] = F[2] + c4 * bforce[2];
+        F[0] = F[0] - ((c1 * stress[0] + c2 * stress[3]) + c3 * stress[5]);
+        F[1] = F[1] - ((c1 * stress[3] + c2 * stress[1]) + c3 * stress[4]);
+        F[2] = F[2] - ((c1 * stress[5] + c2 * stress[4]) + c3 * stress[2]);
+    }
+    return 0;
+}
+
+/* elementutilitieselasticity3D.F:401-482 MassMatrixLinearTetra (one Gauss point intent) */
+ORC_API int orc_mass_matrix_tet(const double *x, const double *y, const double *z, const double *elemData, double *Mlocal)
+{
+    double dens = elemData[2];
+    double param[3] = {0.25, 0.25, 0.25}, gw = (double)(1.0f / 6.0f);
+    double N[4], dNdx[4], dNdy[4], dNdz[4], Jac, K[12][12];
+    memset(K, 0, sizeof K);
+    basis3d_tet(param, x, y, z, N, dNdx, dNdy, dNdz, &Jac);
+    if (Jac < 0.0) return 1;
+    double dvol = gw * (Jac * dens);                   /* :446 */
+    for (int ii = 0; ii < 4; ii++) {
+        double b4 = dvol * N[ii];
+        for (int jj = 0; jj < 4; jj++) {
+            double fact = b4 * N[jj];
+            for (int d = 0; d < 3; d++) K[3 * ii + d][3 * jj + d] = K[3 * ii + d][3 * jj + d] + fact;
+        }
+    }
+    for (int ii = 0; ii < 12; ii++) {
+        double fact = 0.0;
+        for (int jj = 0; jj < 12; jj++) fact = fact + K[ii][jj];
+        Mlocal[ii] = fact;
+    }
+    return 0;
+}
+
+static int explicit_gather(int kind, int e, int nElem, const int *conn, int nNode, const double *coords, double *xn, double *yn,
+                           double *zn, int *nodes)
+{
+    int npe = kind == 2 ? 3 : 4;
+    for (int ii = 0; ii < npe; ii++) {
+        int n1 = conn[(size_t)ii * nElem + e] - 1;      /* np = 1: node_map_get_old is the identity */
+        nodes[ii] = n1;
+        xn[ii] = coords[n1]; yn[ii] = coords[(size_t)nNode + n1];
+        if (kind == 3) zn[ii] = coords[2 * (size_t)nNode + n1];
+    }
+    return npe;
+}
+
+/* triaelasticityexplicit.F:881-921: globalM(node dof) += Mlocal, element by element */
+ORC_API int orc_explicit_lumped_mass(int kind, int nElem, const int *conn, int nNode, const double *coords,
+                                     const double *elemData, double *globalM)
+{
+    int ndof = kind == 2 ? 2 : 3, nbad = 0;
+    for (size_t i = 0; i < (size_t)nNode * ndof; i++) globalM[i] = 0.0;
+    for (int e = 0; e < nElem; e++) {
+        double xn[4], yn[4], zn[4], Ml[12];
+        int nodes[4];
+        int npe = explicit_gather(kind, e, nElem, conn, nNode, coords, xn, yn, zn, nodes);
+        nbad += kind == 2 ? orc_mass_matrix_tria(xn, yn, elemData, Ml) : orc_mass_matrix_tet(xn, yn, zn, elemData, Ml);
+        for (int ii = 0; ii < npe; ii++)
+            for (int d = 0; d < ndof; d++) {
+                size_t g = (size_t)nodes[ii] * ndof + d;
+                globalM[g] = globalM[g] + Ml[ii * ndof + d];
+            }
+    }
+    return nbad;
+}
+
+/* triaelasticityexplicit.F:972-1118: nsteps central-difference steps with constant elemData.  disp == dispPrev on entry  */
+/* (the loop's own invariant after its first pass); free_slots = assyForSoln (1-based node-dof slots of the free dofs).  */
+ORC_API int orc_explicit_advance(int kind, int nElem, const int *conn, int nNode, const double *coords, int size_global,
+                                 const int *free_slots, const double *elemData, const double *timeData, double dt, int nsteps,
+                                 const double *globalM, double *disp, double *dispPrev, double *dispPrev2, double *velo,
+                                 double *acce)
+{
+    int ndof = kind == 2 ? 2 : 3, nbad = 0;
+    size_t nd = (size_t)nNode * ndof;
+    double *rhs = malloc(sizeof(double) * nd);
+    double DTT = dt * dt, IDTT = 1.0 / DTT;            /* :961-962 */
+    for (int step = 0; step < nsteps; step++) {
+        for (size_t i = 0; i < nd; i++) rhs[i] = 0.0;  /* :994 */
+        for (int e = 0; e < nElem; e++) {              /* :996-1057 */
+            double xn[4], yn[4], zn[4], de[12], ve[12], Fl[12];
+            int nodes[4];
+            int npe = explicit_gather(kind, e, nElem, conn, nNode, coords, xn, yn, zn, nodes);
+            for (int ii = 0; ii < npe; ii++)
+                for (int d = 0; d < ndof; d++) {
+                    de[ii * ndof + d] = disp[(size_t)nodes[ii] * ndof + d];
+                    ve[ii * ndof + d] = velo[(size_t)nodes[ii] * ndof + d];
+                }
+            nbad += kind == 2 ? orc_residual_elasticity_tria(xn, yn, elemData, timeData, de, ve, Fl)
+                              : orc_residual_elasticity_tet(xn, yn, zn, elemData, timeData, de, ve, Fl);
+            for (int ii = 0; ii < npe; ii++)
+                for (int d = 0; d < ndof; d++) {
+                    size_t g = (size_t)nodes[ii] * ndof + d;
+                    rhs[g] = rhs[g] + Fl[ii * ndof + d];
+                }
+        }
+        for (int ii = 0; ii < size_global; ii++) {     /* :1072-1079: free dofs only; Dirichlet dofs stay at zero */
+            size_t jj = (size_t)free_slots[ii] - 1;
+            rhs[jj] = rhs[jj] + IDTT * globalM[jj] * (2.0 * dispPrev[jj] - dispPrev2[jj]);
+            disp[jj] = (DTT * rhs[jj]) / globalM[jj];
+        }
+        for (size_t i = 0; i < nd; i++) {              /* :1084-1085, then :1118-1121 */
+            velo[i] = (disp[i] - dispPrev2[i]) / (2.0 * dt);
+            acce[i] = (disp[i] - 2.0 * dispPrev[i] + dispPrev2[i]) / DTT;
+        }
+        for (size_t i = 0; i < nd; i++) { dispPrev2[i] = dispPrev[i]; dispPrev[i] = disp[i]; }
+    }
+    free(rhs);
+    return nbad;
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -192,5 +192,58 @@ def ilu0_solve(rowptr, col, fval, invdiag, r, block_start=None):
     return z
 
 
+# ---- explicit dynamics ----
+
+def residual_elasticity(kind, x, y, z, elemData, timeData, dispC, veloC=None):
+    """ResidualElasticityLinearTria / ...Tetra for one element: (Flocal, jac_negative)."""
+    npe, ndof, ndim = KIND_DIMS[kind]
+    F = np.zeros(npe * ndof)
+    x, y = _f64(x), _f64(y)
+    ed, td, dc = _f64(elemData), _f64(timeData), _f64(dispC)
+    vc = _f64(veloC) if veloC is not None else np.zeros(npe * ndof)
+    if kind == ELASTICITY_TRIA:
+        rc = lib().orc_residual_elasticity_tria(_d(x), _d(y), _d(ed), _d(td), _d(dc), _d(vc), _d(F))
+    else:
+        zz = _f64(z)
+        rc = lib().orc_residual_elasticity_tet(_d(x), _d(y), _d(zz), _d(ed), _d(td), _d(dc), _d(vc), _d(F))
+    return F, rc
+
+
+def mass_matrix(kind, x, y, z, elemData):
+    """MassMatrixLinearTria / ...Tetra for one element: (Mlocal, jac_negative)."""
+    npe, ndof, ndim = KIND_DIMS[kind]
+    Ml = np.zeros(npe * ndof)
+    x, y, ed = _f64(x), _f64(y), _f64(elemData)
+    if kind == ELASTICITY_TRIA:
+        rc = lib().orc_mass_matrix_tria(_d(x), _d(y), _d(ed), _d(Ml))
+    else:
+        zz = _f64(z)
+        rc = lib().orc_mass_matrix_tet(_d(x), _d(y), _d(zz), _d(ed), _d(Ml))
+    return Ml, rc
+
+
+def explicit_lumped_mass(kind, conn, coords, elemData):
+    conn, coords = _i32(conn), _f64(coords)
+    npe, ndof, ndim = KIND_DIMS[kind]
+    M = np.zeros(coords.shape[1] * ndof)
+    nbad = lib().orc_explicit_lumped_mass(kind, conn.shape[1], _i(conn), coords.shape[1], _d(coords), _d(_f64(elemData)), _d(M))
+    return M, nbad
+
+
+def explicit_advance(kind, conn, coords, free_slots, elemData, timeData, dt, nsteps, M, state=None):
+    """nsteps central-difference steps (triaelasticityexplicit.F:972-1121).  state = dict(disp, dispPrev, dispPrev2, velo,
+    acce) is advanced in place (created zeroed when None) and returned."""
+    conn, coords, fs = _i32(conn), _f64(coords), _i32(free_slots)
+    npe, ndof, ndim = KIND_DIMS[kind]
+    nd = coords.shape[1] * ndof
+    if state is None:
+        state = {k: np.zeros(nd) for k in ("disp", "dispPrev", "dispPrev2", "velo", "acce")}
+    nbad = lib().orc_explicit_advance(kind, conn.shape[1], _i(conn), coords.shape[1], _d(coords), fs.size, _i(fs), _d(_f64(elemData)),
+                                      _d(_f64(timeData)), C.c_double(dt), nsteps, _d(M), _d(state["disp"]), _d(state["dispPrev"]),
+                                      _d(state["dispPrev2"]), _d(state["velo"]), _d(state["acce"]))
+    assert nbad == 0
+    return state
+
+
 def num_threads():
     return lib().orc_num_threads()

@@ -20,10 +20,10 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 # element arithmetic must not be contracted into FMAs (bit-faithful to the reference's evaluation order)
-NO_FMA = {"elements.cu", "assembly.cu", "assembly_tiled.cu"}
+NO_FMA = {"elements.cu", "assembly.cu", "assembly_tiled.cu", "explicit.cu"}
 # host-side set-up loops (tile construction) use OpenMP
 OPENMP = {"assembly_tiled.cu"}
-SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "assembly_ctile.cu", "assembly_fast.cu", "cg.cu", "comm.cu", "host_driver.cu",
+SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "assembly_ctile.cu", "assembly_fast.cu", "cg.cu", "comm.cu", "explicit.cu", "host_driver.cu",
            "host_meshio.cu"]
 
 

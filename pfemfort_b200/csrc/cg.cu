@@ -112,19 +112,46 @@ __device__ __forceinline__ void st_ghost_tagged(double *p, double v, unsigned lo
 {
     asm volatile("st.global.relaxed.sys.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
 }
+__device__ __forceinline__ void ld_ghost_raw(const double *p, long long &bits, unsigned long long &tg)
+{
+    asm volatile("ld.global.relaxed.sys.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+}
 __device__ __forceinline__ double ld_ghost_tagged(const double *p, unsigned long long tag, bool &ok)
 {
     long long bits;
     unsigned long long tg;
-    asm volatile("ld.global.relaxed.sys.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+    ld_ghost_raw(p, bits, tg);
     if (tg != tag) {
         const long long t0 = clock64();
         do {
             if (clock64() - t0 > 20000000000LL) { ok = false; break; }     // ~10 s: a dead peer must not hang the GPU
-            asm volatile("ld.global.relaxed.sys.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tg) : "l"(p) : "memory");
+            ld_ghost_raw(p, bits, tg);
         } while (tg != tag);
     }
     return __longlong_as_double(bits);
+}
+// off-diagonal part of one row: sum_q bval[q] * ghost[bcol[q]] in ascending q, the tagged entries loaded four at a time
+// (independent loads in flight; only an entry whose tag is still old is polled again)
+__device__ __forceinline__ double offdiag_row_tagged(const double *__restrict__ bval, const int *__restrict__ bcol, const double *ghost_t,
+                                                     int lo, int hi, unsigned long long tag, bool &ok)
+{
+    double osum = 0.0;
+    int q = lo;
+    for (; q + 4 <= hi; q += 4) {
+        const double *p0 = ghost_t + 2 * (size_t)bcol[q], *p1 = ghost_t + 2 * (size_t)bcol[q + 1];
+        const double *p2 = ghost_t + 2 * (size_t)bcol[q + 2], *p3 = ghost_t + 2 * (size_t)bcol[q + 3];
+        long long b0, b1, b2, b3;
+        unsigned long long t0, t1, t2, t3;
+        ld_ghost_raw(p0, b0, t0); ld_ghost_raw(p1, b1, t1); ld_ghost_raw(p2, b2, t2); ld_ghost_raw(p3, b3, t3);
+        const double g0 = t0 == tag ? __longlong_as_double(b0) : ld_ghost_tagged(p0, tag, ok);
+        const double g1 = t1 == tag ? __longlong_as_double(b1) : ld_ghost_tagged(p1, tag, ok);
+        const double g2 = t2 == tag ? __longlong_as_double(b2) : ld_ghost_tagged(p2, tag, ok);
+        const double g3 = t3 == tag ? __longlong_as_double(b3) : ld_ghost_tagged(p3, tag, ok);
+        osum = fma(bval[q], g0, osum); osum = fma(bval[q + 1], g1, osum);
+        osum = fma(bval[q + 2], g2, osum); osum = fma(bval[q + 3], g3, osum);
+    }
+    for (; q < hi; q++) osum = fma(bval[q], ld_ghost_tagged(ghost_t + 2 * (size_t)bcol[q], tag, ok), osum);
+    return osum;
 }
 
 __device__ __forceinline__ unsigned long long p2p_tag(const CgState *st, int kind)
@@ -1390,6 +1417,7 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 1u);
         if (a.multi && a.halo_tag) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_ghost_tagged(a.send_dst_t[i], pval(a.send_idx[i]), htag);
+            if (a.halo_tag == 2 && gtid < a.n_send) __threadfence_system();      // push the posted stores out now (senders only)
         } else if (a.multi) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], pval(a.send_idx[i]));
             __threadfence_system();
@@ -1435,9 +1463,7 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
                     int lo = 0, hi = 0;
                     if (r < nloc) { lo = a.off_ptr[r]; hi = a.off_ptr[r + 1]; }
                     if (a.halo_tag) {
-                        double osum = 0.0;
-                        for (int q = lo; q < hi; q++) osum = fma(a.bval[q], ld_ghost_tagged(a.ghost_t + 2 * (size_t)a.bcol[q], htag, halo_ok), osum);
-                        sum = sum + osum;
+                        if (hi > lo) sum = sum + offdiag_row_tagged(a.bval, a.bcol, a.ghost_t, lo, hi, htag, halo_ok);
                     } else if (__any_sync(0xffffffffu, hi > lo)) {
                         if (!halo_ready) {       // first boundary slice of this warp in this iteration: wait for the neighbours
                             bool okw = true;
@@ -1603,6 +1629,7 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * round + 1u);
         if (a.multi && a.halo_tag) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_ghost_tagged(a.send_dst_t[i], a.z[a.send_idx[i]], htag);
+            if (a.halo_tag == 2 && gtid < a.n_send) __threadfence_system();
         } else if (a.multi) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_relaxed_sys_f64(a.send_dst[i], a.z[a.send_idx[i]]);
             __threadfence_system();
@@ -1647,9 +1674,7 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
                 int lo = 0, hi = 0;
                 if (r < nloc) { lo = a.off_ptr[r]; hi = a.off_ptr[r + 1]; }
                 if (a.halo_tag) {
-                    double osum = 0.0;
-                    for (int q = lo; q < hi; q++) osum = fma(a.bval[q], ld_ghost_tagged(a.ghost_t + 2 * (size_t)a.bcol[q], htag, halo_ok), osum);
-                    sum = sum + osum;
+                    if (hi > lo) sum = sum + offdiag_row_tagged(a.bval, a.bcol, a.ghost_t, lo, hi, htag, halo_ok);
                 } else if (__any_sync(0xffffffffu, hi > lo)) {
                     if (!halo_ready) {
                         bool okw = true;
@@ -1774,6 +1799,7 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
         // halo flavour: tag-validated 16-byte entries (default) or values + per-neighbour flags (PFEM_PCG_HALO=flag)
         const char *henv = getenv("PFEM_PCG_HALO");
         a.halo_tag = (a.multi && h->send_dst_t.p && !(henv && strcmp(henv, "flag") == 0)) ? 1 : 0;
+        if (a.halo_tag && henv && strcmp(henv, "tagf") == 0) a.halo_tag = 2;      // + a system fence by the sending threads
         a.ghost_t = h->ghost_buf.p + h->ghost_tag_off;
         a.send_dst_t = h->send_dst_t.p;
     }

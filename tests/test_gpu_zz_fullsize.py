@@ -1,5 +1,9 @@
-"""Full-size runs of the BASELINE.json configurations C2, C4 and C5 on one GPU, checked through size-independent
-properties (the oracle cannot assemble 48 M elements in seconds):
+"""Full-size runs of the BASELINE.json configurations C2, C4 and C5 on one GPU, checked
+
+(1) value by value against the CPU oracle: the single-thread `orc_assemble` (sequential reference element order, ~6 s for
+    the 48 M tets of C5) on the GPU-built pattern -- matrix values and RHS must be bit-identical (`array_equal`) on the
+    default value pass -- and, for C2, the oracle's CG iteration count at full size;
+(2) through size-independent properties:
 
 * pattern size equal to the closed-form count of SURVEY.md section 8 (N + 2 x free-node edges);
 * symmetry of the assembled operator (x'Ay == y'Ax to rounding for random x, y);
@@ -14,6 +18,7 @@ The same property checks run on the CPU oracle at small sizes in tests/test_orac
 import numpy as np
 import pytest
 
+from oracle import pyoracle as O
 from pfemfort_b200 import driver as D, mesh as M, solver as S
 from properties import nnz_tet_poisson, nnz_tria_poisson, symmetric_to_rounding
 
@@ -35,6 +40,13 @@ def _passes(m, kind, num, ed2):
     s.assemble(ed2, D.DEFAULT_TIMEDATA)
     v2 = s.get_csr(values=True)[2]
     assert np.array_equal(v2, 2.0 * v1), "doubling the material constant must double every entry exactly"
+    # value level, full size: the sequential oracle on the same pattern (the pattern itself is pinned by its closed-form size,
+    # sortedness and the symmetric probe; at small and mid sizes it is compared entry by entry in test_gpu_parity.py)
+    oval, orhs, nbad = O.assemble(kind, num.conn_new, m.coords, None, num.elemDof, num.solnApplied, D.DEFAULT_ELEMDATA[kind],
+                                  D.DEFAULT_TIMEDATA, rp, col)
+    assert nbad == 0
+    assert np.array_equal(v1, oval), "full-size matrix values differ from the sequential oracle"
+    assert np.array_equal(r1, orhs), "full-size RHS differs from the sequential oracle"
     return s, rp, col, v1
 
 
@@ -70,6 +82,8 @@ def test_c2_tria1000_poisson_full_size(gpu):
     s = S.SolverB200(0)
     info = D.run_rank(s, m, num, rtol=1e-10)
     assert info["reason"] == 2 and abs(info["its"] - 1442) <= ITS_TOL * 1442
+    _, oits, oreason, _ = O.cg_jacobi(rp, col, val, s.get_rhs(), rtol=1e-10, threads=O.num_threads())
+    assert oreason == 2 and abs(info["its"] - oits) <= ITS_TOL * oits, (info["its"], oits)
     u = D.nodal_solution(num, s.get_solution())[0]
     assert np.abs(u - M.exact_poisson_tria(m.coords[0], m.coords[1])).max() < 1e-6
     s.free()
