@@ -203,7 +203,8 @@ int main(int argc, char **argv)
     for (size_t b = 0; b < fbc_node.size(); b++) {                 // tetraelasticityparallelimpl1.F:971-982
         const int n1n = map_new[fbc_node[b] - 1];
         const int row = (n1n - 1) * ndof + fbc_dof[b] - 1;
-        if (row >= 1 && row < size_global) CHECK(pfem_solver_add_value(solver, row, fbc_val[b]));
+        // every admissible row is added once overall (the reference: range test + PETSc stash); here by the rank that owns it
+        if (row >= 1 && row < size_global && row >= row_lo && row < row_hi) CHECK(pfem_solver_add_value(solver, row, fbc_val[b]));
     }
     printf(" Solving the matrix system \n");
     CHECK(pfem_solver_factorise_and_solve(solver));

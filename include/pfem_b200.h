@@ -34,7 +34,9 @@ enum {
     PFEM_ERR_NEG_JACOBIAN = 4,  /* the reference STOPs (elementutilitiespoisson.F:71,157; elasticity2D.F:90; elasticity3D.F:320) */
     PFEM_ERR_NCCL = 5,
     PFEM_ERR_SIZE = 6,          /* 32-bit index range exceeded */
-    PFEM_ERR_NUMBERING = 7      /* inconsistent dof numbering (tetrapoissonparallelimpl1.F:614-616,650-655) */
+    PFEM_ERR_NUMBERING = 7,     /* inconsistent dof numbering (tetrapoissonparallelimpl1.F:614-616,650-655) */
+    PFEM_ERR_PATTERN = 8        /* a slow-path add hit a matrix location the pattern pass did not create (PETSc would insert it under
+                                   MAT_NEW_NONZERO_LOCATIONS, solverpetsc.F:171; here the structure is fixed): reported, never dropped silently */
 };
 
 /* solver states, solverpetsc.F:64-68 */

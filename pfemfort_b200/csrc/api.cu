@@ -145,13 +145,17 @@ int pfem_solver_create(pfem_solver_t **out, int device, int rank, int nranks, co
     if (!h) { set_error("out of host memory"); return PFEM_ERR_ARG; }
     h->device = device; h->rank = rank; h->nranks = nranks;
     h->sm_count = prop.multiProcessorCount;
-    PFEM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    PFEM_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-    PFEM_CUDA(cudaEventCreate(&h->ev0));
-    PFEM_CUDA(cudaEventCreate(&h->ev1));
-    PFEM_CUDA(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
-    PFEM_CUDA(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
-    int st = comm_init(h, nccl_id128);
+    // any failure from here on releases the half-built handle (streams / events already created) before returning
+    auto make = [&]() -> int {
+        PFEM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        PFEM_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        PFEM_CUDA(cudaEventCreate(&h->ev0));
+        PFEM_CUDA(cudaEventCreate(&h->ev1));
+        PFEM_CUDA(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+        PFEM_CUDA(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+        return comm_init(h, nccl_id128);
+    };
+    const int st = make();
     if (st != PFEM_OK) { pfem_solver_free(h); return st; }
     *out = h;
     return PFEM_OK;
@@ -298,6 +302,7 @@ int pfem_solver_set_zero(pfem_solver_t *h)
     PFEM_CUDA(cudaMemsetAsync(h->rhs.p, 0, (size_t)(h->size_local > 0 ? h->size_local : 1) * sizeof(double), h->stream));
     PFEM_CUDA(cudaStreamSynchronize(h->stream));
     h->values_zero = true; h->rhs_zero = true;
+    for (auto &st : h->stash) st.clear();     // setZero assembles and then zeroes (solverpetsc.F:228-239): stashed adds vanish with it
     return PFEM_OK;
 }
 
@@ -390,6 +395,7 @@ int pfem_solver_solve(pfem_solver_t *h)
         set_error("Factorise matrix first before solving it!");
         return PFEM_ERR_STATE;
     }
+    PFEM_TRY(stash_flush(h));                            // MatAssemblyBegin/End, VecAssemblyBegin/End (solverpetsc.F:447-468)
     return cg_solve(h);
 }
 

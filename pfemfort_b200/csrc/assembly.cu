@@ -267,16 +267,22 @@ int assemble_values(pfem_solver *h, const double *elemData, const double *timeDa
 }
 
 // ---- slow-path adds: MatSetValues / VecSetValues / MatSetValue mirrors ----------------------------------------
-// One thread walks the block in PETSc's order (row by row, column by column).
+// One thread walks the block in PETSc's order (row by row, column by column).  Rows of this rank are added in place;
+// rows owned by another rank are NOT dropped: like PETSc's stash they are kept on the host and shipped to their owner
+// at the next assembly point (stash_flush, called by pfem_solver_solve = MatAssemblyBegin/End of solverpetsc.F:447-468),
+// where they are added in arrival order (source rank ascending, call order within a rank).  A location that the pattern
+// pass did not create cannot be inserted later (the structure is fixed; PETSc would allocate it under
+// MAT_NEW_NONZERO_LOCATIONS): it is counted and reported as PFEM_ERR_PATTERN, never skipped silently.
 __global__ void add_entries_kernel(int n, const int *__restrict__ rows, const int *__restrict__ cols,
                                    const double *__restrict__ vals, int transposed, const double *__restrict__ F,
                                    int row_lo, int row_hi, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                   double *__restrict__ val, double *__restrict__ rhs)
+                                   double *__restrict__ val, double *__restrict__ rhs, int *__restrict__ off_pattern)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int missed = 0;
     for (int i = 0; i < n; i++) {
         const int r = rows[i];
-        if (r < row_lo || r >= row_hi) continue;   // negative rows are dropped; other ranks' rows are theirs to add
+        if (r < row_lo || r >= row_hi) continue;   // negative rows are dropped like PETSc does; other ranks' rows went to the stash
         const int lr = r - row_lo;
         if (F) rhs[lr] = rhs[lr] + F[i];
         if (!vals) continue;
@@ -292,23 +298,77 @@ __global__ void add_entries_kernel(int n, const int *__restrict__ rows, const in
             if (lo < end && col[lo] == c) {
                 const double v = transposed ? vals[j + n * i] : vals[i + n * j];
                 val[lo] = val[lo] + v;
+            } else {
+                missed++;
             }
-            // a location outside the pattern would be a new nonzero: the pattern pass fixed the structure
         }
     }
+    if (missed) atomicAdd(off_pattern, missed);
+}
+
+// stashed (row, col, value) triples received from the other ranks, in arrival order; col < 0: right-hand side entry
+__global__ void add_triples_kernel(int n, const int *__restrict__ t, int row_lo, int row_hi, const int *__restrict__ rowptr,
+                                   const int *__restrict__ col, double *__restrict__ val, double *__restrict__ rhs,
+                                   int *__restrict__ off_pattern)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int missed = 0;
+    for (int k = 0; k < n; k++) {
+        const int r = t[4 * k], c = t[4 * k + 1];
+        const double v = __hiloint2double(t[4 * k + 3], t[4 * k + 2]);
+        if (r < row_lo || r >= row_hi) { missed++; continue; }
+        const int lr = r - row_lo;
+        if (c < 0) { rhs[lr] = rhs[lr] + v; continue; }
+        int lo = rowptr[lr], hi = rowptr[lr + 1];
+        const int end = hi;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (col[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo < end && col[lo] == c) val[lo] = val[lo] + v; else missed++;
+    }
+    if (missed) atomicAdd(off_pattern, missed);
+}
+
+static void stash_push(pfem_solver *h, int owner, int row, int col, double v)
+{
+    long long bits;
+    memcpy(&bits, &v, sizeof bits);
+    std::vector<int> &st = h->stash[owner];
+    st.push_back(row); st.push_back(col);
+    st.push_back((int)(bits & 0xffffffffLL)); st.push_back((int)((bits >> 32) & 0xffffffffLL));
 }
 
 int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const double *vals, bool transposed,
                 const double *F)
 {
     if (n <= 0 || !rows) { set_error("add: bad argument"); return PFEM_ERR_ARG; }
+    if (vals && !cols) { set_error("add: cols missing"); return PFEM_ERR_ARG; }
+    for (int i = 0; i < n; i++)
+        if (rows[i] >= h->size_global || (vals && cols[i] >= h->size_global)) {      // PETSc: "Row too large" / "Column too large"
+            set_error("add: index %d outside the global system (size %d)", rows[i] >= h->size_global ? rows[i] : cols[i], h->size_global);
+            return PFEM_ERR_ARG;
+        }
+    // rows of other ranks: stash (MatSetValues / VecSetValues on an off-process row)
+    if (h->nranks > 1) {
+        if ((int)h->stash.size() != h->nranks) h->stash.assign(h->nranks, std::vector<int>());
+        for (int i = 0; i < n; i++) {
+            const int r = rows[i];
+            if (r < 0 || (r >= h->row_lo && r < h->row_hi)) continue;
+            int owner = 0;
+            while (owner + 1 < h->nranks && r >= h->row_starts[owner + 1]) owner++;
+            if (F) stash_push(h, owner, r, -1, F[i]);
+            if (vals)
+                for (int j = 0; j < n; j++)
+                    if (cols[j] >= 0) stash_push(h, owner, r, cols[j], transposed ? vals[j + (size_t)n * i] : vals[i + (size_t)n * j]);
+        }
+    }
     DevBuf<int> dr, dc;
     DevBuf<double> dv, df;
     cudaStream_t s = h->stream;
     PFEM_TRY(dr.alloc(n));
     PFEM_CUDA(cudaMemcpyAsync(dr.p, rows, n * sizeof(int), cudaMemcpyHostToDevice, s));
     if (vals) {
-        if (!cols) { set_error("add: cols missing"); return PFEM_ERR_ARG; }
         PFEM_TRY(dc.alloc(n));
         PFEM_TRY(dv.alloc((size_t)n * n));
         PFEM_CUDA(cudaMemcpyAsync(dc.p, cols, n * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -318,13 +378,64 @@ int add_entries(pfem_solver *h, int n, const int *rows, const int *cols, const d
         PFEM_TRY(df.alloc(n));
         PFEM_CUDA(cudaMemcpyAsync(df.p, F, n * sizeof(double), cudaMemcpyHostToDevice, s));
     }
+    PFEM_CUDA(cudaMemsetAsync(h->neg_count.p, 0, sizeof(int), s));
     add_entries_kernel<<<1, 32, 0, s>>>(n, dr.p, vals ? dc.p : nullptr, vals ? dv.p : nullptr, transposed ? 1 : 0,
-                                        F ? df.p : nullptr, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, h->val.p, h->rhs.p);
+                                        F ? df.p : nullptr, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, h->val.p, h->rhs.p,
+                                        h->neg_count.p);
     h->launches++;
     PFEM_CUDA(cudaGetLastError());
+    int missed = 0;
+    PFEM_CUDA(cudaMemcpyAsync(&missed, h->neg_count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     PFEM_CUDA(cudaStreamSynchronize(s));
     if (vals) h->values_zero = false;
     if (F) h->rhs_zero = false;
+    if (missed) {
+        h->off_pattern_total += missed;
+        set_error("add: %d matrix location(s) are not in the pattern built by the pattern pass (new nonzero locations cannot be "
+                  "inserted after it; entries inside the pattern were added)", missed);
+        return PFEM_ERR_PATTERN;
+    }
+    return PFEM_OK;
+}
+
+// MatAssemblyBegin/End + VecAssemblyBegin/End (solverpetsc.F:447-468) for the slow-path adds: collective over the ranks.
+int stash_flush(pfem_solver *h)
+{
+    if (h->nranks == 1) return PFEM_OK;
+    if ((int)h->stash.size() != h->nranks) h->stash.assign(h->nranks, std::vector<int>());
+    int mine = 0;
+    for (int q = 0; q < h->nranks; q++) mine += (int)(h->stash[q].size() / 4);
+    std::vector<int> all;
+    PFEM_TRY(comm_allgather_int(h, mine, all));
+    long long total = 0;
+    for (int v : all) total += v;
+    if (total == 0) return PFEM_OK;
+    std::vector<int> sendbuf, sendcounts(h->nranks, 0), recvbuf, recvcounts;
+    for (int q = 0; q < h->nranks; q++) {
+        sendcounts[q] = (int)h->stash[q].size();
+        sendbuf.insert(sendbuf.end(), h->stash[q].begin(), h->stash[q].end());
+        h->stash[q].clear();
+    }
+    PFEM_TRY(comm_alltoallv_int(h, sendbuf, sendcounts, recvbuf, recvcounts));
+    const int ntrip = (int)(recvbuf.size() / 4);
+    h->stash_received += ntrip;
+    if (ntrip == 0) return PFEM_OK;
+    cudaStream_t s = h->stream;
+    DevBuf<int> dt;
+    PFEM_TRY(dt.alloc(recvbuf.size()));
+    PFEM_CUDA(cudaMemcpyAsync(dt.p, recvbuf.data(), recvbuf.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    PFEM_CUDA(cudaMemsetAsync(h->neg_count.p, 0, sizeof(int), s));
+    add_triples_kernel<<<1, 32, 0, s>>>(ntrip, dt.p, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, h->val.p, h->rhs.p, h->neg_count.p);
+    h->launches++;
+    int missed = 0;
+    PFEM_CUDA(cudaMemcpyAsync(&missed, h->neg_count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PFEM_CUDA(cudaStreamSynchronize(s));
+    h->values_zero = false; h->rhs_zero = false;
+    if (missed) {
+        h->off_pattern_total += missed;
+        set_error("assembly: %d stashed entr(ies) from other ranks are not in this rank's pattern", missed);
+        return PFEM_ERR_PATTERN;
+    }
     return PFEM_OK;
 }
 

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(256) ct_records_kernel(int pass, int TR, int n
         return;
     }
     // ---- number the halo nodes in ascending node id: compact, bitonic sort, write ranks back into the table ----
+    __syncthreads();                     // every thread has read nh = s_count before thread 0 resets it (racecheck, r02)
     if (tid == 0) s_count = 0;
     int npad = 1;
     while (npad < nh) npad <<= 1;

@@ -187,6 +187,9 @@ struct pfem_solver {
     // halo plan
     std::vector<int> send_counts, recv_counts, send_displs, recv_displs;
     pfem::DevBuf<int> send_idx;            // local row indices to pack, grouped by destination rank
+    // slow-path adds: off-rank (row, col, value) triples per owner (4 ints each), shipped at the next assembly point
+    std::vector<std::vector<int>> stash;
+    long long off_pattern_total = 0, stash_received = 0;
     pfem::DevBuf<double> send_buf, ghost_buf;
     size_t ghost_tag_off = 0;                     // ghost_buf: offset (in doubles) of the tagged {value, tag} entries
     pfem::DevBuf<double *> send_dst_t;            // per packed halo entry: address of the peer's tagged ghost entry
@@ -247,6 +250,7 @@ int comm_unique_id(void *id128);
 int comm_init(pfem_solver *h, const void *id128);
 void comm_destroy(pfem_solver *h);
 int comm_allgather_int(pfem_solver *h, int value, std::vector<int> &out);
+int stash_flush(pfem_solver *h);
 int comm_alltoallv_int(pfem_solver *h, const std::vector<int> &sendbuf, const std::vector<int> &sendcounts,
                        std::vector<int> &recvbuf, std::vector<int> &recvcounts);
 int comm_halo_exchange(pfem_solver *h, const double *sendbuf, double *recvbuf, cudaStream_t s);

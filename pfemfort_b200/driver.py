@@ -157,7 +157,11 @@ def run_rank(solver: S.SolverB200, mesh: Mesh, num: Numbering, rank: int = 0, el
     if apply_force_bc and mesh.fbc_node.size:
         rows, vals = force_bc_rows(mesh, num, ndof, fix_forcebc)
         for r, v in zip(rows, vals):
-            solver.add_value(r, v)                # rows outside this rank's block are skipped by the library
+            # the reference range-tests the row before VecSetValue (tetraelasticityparallelimpl1.F:977); with its stash every
+            # admissible row is added exactly once overall: here by its owner (a row handed to a non-owner would be stashed and
+            # shipped to the owner at the next solve, like PETSc does -- and then count twice)
+            if lo <= r < hi:
+                solver.add_value(r, v)
     if do_solve:
         solver.factoriseAndSolve()
     return solver.info()

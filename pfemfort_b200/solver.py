@@ -20,7 +20,7 @@ POISSON_TRIA, POISSON_TETRA, ELASTICITY_TRIA, ELASTICITY_TETRA = 0, 1, 2, 3
 KIND_DIMS = {0: (3, 1, 2), 1: (4, 1, 3), 2: (3, 2, 2), 3: (4, 3, 3)}   # npElem, ndof, ndim
 PC_NONE, PC_JACOBI, PC_BJACOBI_ILU0 = 0, 1, 2     # PC_BJACOBI_ILU0: the reference's default (solverpetsc.F:206)
 
-OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NEG_JACOBIAN, ERR_NCCL, ERR_SIZE, ERR_NUMBERING = range(8)
+OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NEG_JACOBIAN, ERR_NCCL, ERR_SIZE, ERR_NUMBERING, ERR_PATTERN = range(9)
 SOLVER_EMPTY, PATTERN_OK, INIT_OK, ASSEMBLY_OK, FACTORISE_OK = 1, 2, 3, 4, 5
 
 

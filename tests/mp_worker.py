@@ -79,6 +79,47 @@ def main():
             result["rhs_bit_identical"] = bool(np.array_equal(np.concatenate(rhss), grhs))
             result["nnz"] = int(gcol.size)
             result["local_elements"] = int(lst.size)
+    elif a.mode == "stash":
+        # slow-path adds on rows of OTHER ranks (MatSetValues / VecSetValues on off-process rows): stashed, shipped to the
+        # owner at the next assembly point (solve), added there.  Every rank adds the block (rank+1) * ones on the dofs of
+        # a few interface elements; the gathered system must equal the batched assembly + the sum of all ranks' blocks.
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(S.comm_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(idt, 0)
+        s = S.SolverB200(device=local_rank, rank=rank, nranks=world, nccl_id=bytes(idt.numpy().tobytes()))
+        D.run_rank(s, m, num, rank=rank, rtol=1e-10, do_solve=False)
+        owner = np.searchsorted(np.array([num.row_range(q)[1] for q in range(world)]), np.maximum(num.elemDof, 0), side="right")
+        free = num.elemDof >= 0
+        mixed = [e for e in range(num.elemDof.shape[1]) if free[:, e].all() and len(set(owner[:, e])) > 1][:5]
+        for e in mixed:
+            dofs = num.elemDof[:, e]
+            n = dofs.size
+            s.add_matrix(dofs, dofs, np.full((n, n), float(rank + 1)))
+            s.add_vector(dofs, np.full(n, 10.0 * (rank + 1)))
+        s.factoriseAndSolve()                       # assembly point: the stash travels here
+        rp, col, val = s.get_csr()
+        rhs = s.get_rhs()
+        parts = [None] * world
+        dist.all_gather_object(parts, (rp, col, val, rhs))
+        if rank == 0:
+            grp, gcol = O.pattern(num.elemDof, num.size_global)
+            gval, grhs, _ = O.assemble(kind, num.conn_new, m.coords, num.node_map_get_old, num.elemDof, num.solnApplied,
+                                       D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, grp, gcol)
+            if m.fbc_node.size:
+                O.add_force_bc(grhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, num.node_map_get_new, num.NodeDofArrayNew, num.size_global)
+            tot = float(sum(range(1, world + 1)))
+            for e in mixed:
+                dofs = num.elemDof[:, e]
+                for i in dofs:
+                    grhs[i] += 10.0 * tot
+                    for j in dofs:
+                        k = grp[i] + int(np.searchsorted(gcol[grp[i]:grp[i + 1]], j))
+                        gval[k] += tot
+            result["mixed_elements"] = len(mixed)
+            result["values_match"] = bool(np.allclose(np.concatenate([p[2] for p in parts]), gval, rtol=1e-13, atol=1e-13))
+            result["rhs_match"] = bool(np.allclose(np.concatenate([p[3] for p in parts]), grhs, rtol=1e-13, atol=1e-13))
+        s.free()
     else:
         idt = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:

@@ -85,3 +85,20 @@ def test_multi_gpu_bjacobi_ilu0(gpu, tmp_path, mesh, nproc, port, comm):
     assert all(x == res["oracle_reason"] == 2 for x in res["reason"]) and len(set(res["its"])) == 1
     assert abs(res["its"][0] - res["oracle_its"]) <= max(1, 0.02 * res["oracle_its"])
     assert res["solution_rel_err"] < 1e-7
+
+
+@pytest.mark.parametrize("mesh,nproc,port", [("tet10", 2, 29671), ("cookmembranetria32", 2, 29672), ("gen_tet24", 4, 29673)])
+def test_multi_gpu_slow_path_stash(gpu, tmp_path, mesh, nproc, port):
+    """MatSetValues / VecSetValues mirrors on rows owned by ANOTHER rank are stashed and shipped to the owner at the next
+    assembly point, like PETSc's stash (solverpetsc.F:447-468): nothing is dropped."""
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    out = os.path.join(str(tmp_path), "result.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), "--mode", "stash", "--mesh", mesh, "--out", out]
+    env = dict(os.environ)
+    env.pop("PFEM_ASM", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.load(open(out))
+    assert res["mixed_elements"] > 0 and res["values_match"] and res["rhs_match"], res

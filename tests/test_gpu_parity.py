@@ -517,3 +517,28 @@ def test_default_pc_is_the_references_and_options_file(gpu, input_dir, tmp_path)
         s.set_options_from_file(str(opt))
     s.set_options_from_file(str(tmp_path / "absent.dat"))          # no file: defaults stay
     s.free()
+
+
+def test_slow_path_never_drops_silently(gpu, input_dir):
+    """A MatSetValues-style add on a location the pattern pass did not create is reported (PFEM_ERR_PATTERN), an index beyond
+    the global system is an argument error (PETSc: 'Row too large'); negative indices are skipped like PETSc does."""
+    m, kind = _load("tet10", input_dir)
+    num = D.number(m, kind)
+    s = S.SolverB200(0)
+    D.run_rank(s, m, num, do_solve=False)
+    rp, col, v0 = s.get_csr()
+    far = int(np.setdiff1d(np.arange(num.size_global), col[rp[0]:rp[1]])[0])       # a dof not coupled with dof 0
+    with pytest.raises(S.PfemError) as ei:
+        s.add_matrix([0, far], [0, far], np.ones((2, 2)))
+    assert ei.value.status == S.ERR_PATTERN
+    v1 = s.get_csr()[2]
+    k00 = rp[0] + int(np.searchsorted(col[rp[0]:rp[1]], 0))
+    assert v1[k00] == v0[k00] + 1.0                                                # the entries inside the pattern were added
+    with pytest.raises(S.PfemError) as ei:
+        s.add_vector([num.size_global], [1.0])
+    assert ei.value.status == S.ERR_ARG
+    r0 = s.get_rhs()
+    s.add_matrix([-1, 0], [-1, 0], np.full((2, 2), 2.0))                           # negative row / column: dropped, no error
+    s.add_vector([-1], [5.0])
+    assert np.array_equal(s.get_rhs(), r0) and s.get_csr()[2][k00] == v0[k00] + 3.0
+    s.free()
