@@ -255,6 +255,29 @@ int pfem_explicit_get_state(pfem_explicit_t *ex, double *disp, double *dispPrev2
 int pfem_explicit_set_state(pfem_explicit_t *ex, const double *disp, const double *dispPrev2);
 int pfem_explicit_get_info(pfem_explicit_t *ex, long long *steps, long long *launches, double *t_advance);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Driver set-up loops on the GPU.  Host arrays in, host arrays out, the work in between
+ * as sorts / scans / gathers on `device`; outputs are bit-identical to the sequential loops of the drivers.
+ * Negative return = -status.
+ *   pfem_gpu_number_dofs    tetrapoissonparallelimpl1.F:357-367 (free dofs), :402-421 (np = 1), :500-677 (node renumbering by
+ *                           partition, NodeDofArrayNew, row ranges, applied values re-keyed).  All node ids 1-based;
+ *                           NodeDofArrayNew column-major nNode x ndof (0 = Dirichlet); part_info [nparts][5] = node_start,
+ *                           node_end, row_start, row_end (1-based, inclusive), size_local.  Returns size_global.
+ *   pfem_gpu_renumber_conn  :659-664, in place.
+ *   pfem_gpu_elem_dof_array :698-713 ElemDofArray (SoA [nsize][nElem], 0-based, -1 = Dirichlet), :722-734 assyForSoln
+ *                           (NULL to skip) and, with list != NULL, the owned + overlap elements of the row block
+ *                           [row_lo, row_hi) in ascending id; returns their count.
+ *   pfem_gpu_gen_tetra      genTetra.cpp:194-334 (nodes, 6 tets per cell) + :497-525 (Dirichlet rows) for the box mesh;
+ *                           ax/ay/az are the accumulated axis coordinates; coords == NULL returns the number of Dirichlet rows. */
+int pfem_gpu_number_dofs(int device, int nNode, int ndof, int nDBC, const int *dbc_node, const int *dbc_dof, const double *dbc_val,
+                         int nparts, const int *node_proc_id, int *node_map_get_old, int *node_map_get_new, int *NodeDofArrayNew,
+                         double *solnApplied, int *part_info);
+int pfem_gpu_renumber_conn(int device, long long n_entries, int *conn, int nNode, const int *node_map_get_new);
+int pfem_gpu_elem_dof_array(int device, int nElem, int npElem, int ndof, int nNode, const int *conn_new, const int *NodeDofArrayNew,
+                            int size_global, int *elemDof, int *assyForSoln, int row_lo, int row_hi, int *list);
+long long pfem_gpu_gen_tetra(int device, int nEx, int nEy, int nEz, const double *ax, const double *ay, const double *az, int dbc_mode,
+                             int ndof, double *coords, int *conn, int *dbc_node, int *dbc_dof, double *dbc_val);
+
 #ifdef __cplusplus
 }
 #endif

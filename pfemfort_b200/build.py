@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unus
 NO_FMA = {"elements.cu", "assembly.cu", "assembly_tiled.cu", "explicit.cu"}
 # host-side set-up loops (tile construction) use OpenMP
 OPENMP = {"assembly_tiled.cu"}
-SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "assembly_ctile.cu", "assembly_fast.cu", "cg.cu", "comm.cu", "explicit.cu", "host_driver.cu",
+SOURCES = ["api.cu", "elements.cu", "pattern.cu", "assembly.cu", "assembly_tiled.cu", "assembly_ctile.cu", "assembly_fast.cu", "cg.cu", "comm.cu", "explicit.cu", "gpu_setup.cu", "host_driver.cu",
            "host_meshio.cu"]
 
 

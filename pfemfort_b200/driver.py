@@ -71,7 +71,11 @@ def partition(mesh: Mesh, kind: int, nparts: int):
     return epart, npart
 
 
-def number(mesh: Mesh, kind: int, nparts: int = 1, node_proc_id=None) -> Numbering:
+def number(mesh: Mesh, kind: int, nparts: int = 1, node_proc_id=None, on_gpu: bool = False, device: int = 0) -> Numbering:
+    """The drivers' numbering block (tetrapoissonparallelimpl1.F:357-734).  on_gpu=True runs it as sorts / scans / gathers on
+    the GPU (csrc/gpu_setup.cu); the outputs are bit-identical (tests/test_gpu_setup.py)."""
+    if on_gpu:
+        return _number_gpu(mesh, kind, nparts, node_proc_id, device)
     lib = S.load_library()
     npe, ndof, ndim = S.KIND_DIMS[kind]
     nNode, nElem = mesh.nNode, mesh.nElem
@@ -92,6 +96,51 @@ def number(mesh: Mesh, kind: int, nparts: int = 1, node_proc_id=None) -> Numberi
     edof = np.zeros((npe * ndof, nElem), np.int32)
     lib.pfem_host_elem_dof_array(nElem, npe, ndof, nNode, _ip(conn_new), _ip(nda), _ip(edof))
     return Numbering(kind, max(nparts, 1), sg, old, new, nda, applied, info, conn_new, edof)
+
+
+def _number_gpu(mesh: Mesh, kind: int, nparts: int, node_proc_id, device: int) -> Numbering:
+    lib = S.load_library()
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    nNode, nElem = mesh.nNode, mesh.nElem
+    old = np.zeros(nNode, np.int32)
+    new = np.zeros(nNode, np.int32)
+    nda = np.zeros((ndof, nNode), np.int32)
+    applied = np.zeros(nNode * ndof)
+    info = np.zeros((max(nparts, 1), 5), np.int32)
+    dn, dd, dv = (np.ascontiguousarray(mesh.dbc_node, np.int32), np.ascontiguousarray(mesh.dbc_dof, np.int32),
+                  np.ascontiguousarray(mesh.dbc_val, np.float64))
+    npid = np.ascontiguousarray(node_proc_id, np.int32) if (node_proc_id is not None and nparts > 1) else None
+    sg = lib.pfem_gpu_number_dofs(device, nNode, ndof, dn.size, _ip(dn), _ip(dd), _dp(dv), nparts, _ip(npid), _ip(old), _ip(new),
+                                  _ip(nda), _dp(applied), _ip(info))
+    if sg < 0:
+        raise S.PfemError(-sg, lib.pfem_last_error().decode())
+    conn_new = np.ascontiguousarray(mesh.conn, np.int32).copy()
+    rc = lib.pfem_gpu_renumber_conn(device, C.c_longlong(conn_new.size), _ip(conn_new), nNode, _ip(new))
+    if rc < 0:
+        raise S.PfemError(-rc, lib.pfem_last_error().decode())
+    edof = np.zeros((npe * ndof, nElem), np.int32)
+    rc = lib.pfem_gpu_elem_dof_array(device, nElem, npe, ndof, nNode, _ip(conn_new), _ip(nda), sg, _ip(edof), None, 0, 0, None)
+    if rc < 0:
+        raise S.PfemError(-rc, lib.pfem_last_error().decode())
+    return Numbering(kind, max(nparts, 1), sg, old, new, nda, applied, info, conn_new, edof)
+
+
+def gpu_local_elements_and_assy(num: Numbering, rank: int, device: int = 0):
+    """(owned + overlap elements of the rank, assyForSoln) formed on the GPU."""
+    lib = S.load_library()
+    npe, ndof, ndim = S.KIND_DIMS[num.kind]
+    lo, hi = num.row_range(rank)
+    nsize, nElem = num.elemDof.shape
+    nNode = num.NodeDofArrayNew.shape[1]
+    edof = np.zeros((nsize, nElem), np.int32)
+    assy = np.zeros(num.size_global, np.int32)
+    lst = np.zeros(nElem, np.int32)
+    n = lib.pfem_gpu_elem_dof_array(device, nElem, npe, ndof, nNode, _ip(np.ascontiguousarray(num.conn_new, np.int32)),
+                                    _ip(np.ascontiguousarray(num.NodeDofArrayNew, np.int32)), num.size_global, _ip(edof), _ip(assy),
+                                    lo, hi, _ip(lst))
+    if n < 0:
+        raise S.PfemError(-n, lib.pfem_last_error().decode())
+    return lst[:n].copy(), assy, edof
 
 
 def local_elements(num: Numbering, rank: int) -> np.ndarray:

@@ -209,6 +209,31 @@ def gen_tetra(x0, x1, nEx, y0, y1, nEy, z0, z1, nEz, dbc: str = "poisson", ndof:
     return Mesh(coords, conn, dn, dd, dv, name=f"tet{nEx}x{nEy}x{nEz}")
 
 
+def gen_tetra_gpu(x0, x1, nEx, y0, y1, nEy, z0, z1, nEz, dbc: str = "poisson", ndof: int = 1, device: int = 0) -> Mesh:
+    """gen_tetra on the GPU (csrc/gpu_setup.cu, pfem_gpu_gen_tetra): only the per-axis accumulation `xx += dx` (n+1 values per
+    axis) runs on the host; nodes, tets and Dirichlet rows are formed by kernels.  Bit-identical to gen_tetra."""
+    import ctypes as C
+
+    from . import solver as S
+    lib = S.load_library()
+    lib.pfem_gpu_gen_tetra.restype = C.c_longlong
+    ax, ay, az = _accumulate(x0, x1, nEx), _accumulate(y0, y1, nEy), _accumulate(z0, z1, nEz)
+    mode = {"poisson": 0, "clamp_y0": 1}[dbc]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None   # noqa: E731
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None      # noqa: E731
+    nrows = lib.pfem_gpu_gen_tetra(device, nEx, nEy, nEz, dp(ax), dp(ay), dp(az), mode, ndof, None, None, None, None, None)
+    if nrows < 0:
+        raise S.PfemError(int(-nrows), lib.pfem_last_error().decode())
+    nN, nE = (nEx + 1) * (nEy + 1) * (nEz + 1), 6 * nEx * nEy * nEz
+    coords = np.zeros((3, nN))
+    conn = np.zeros((4, nE), np.int32)
+    dn, dd, dv = np.zeros(nrows, np.int32), np.zeros(nrows, np.int32), np.zeros(nrows)
+    rc = lib.pfem_gpu_gen_tetra(device, nEx, nEy, nEz, dp(ax), dp(ay), dp(az), mode, ndof, dp(coords), ip(conn), ip(dn), ip(dd), dp(dv))
+    if rc < 0:
+        raise S.PfemError(int(-rc), lib.pfem_last_error().decode())
+    return Mesh(coords, conn, dn, dd, dv, name=f"tet{nEx}x{nEy}x{nEz}")
+
+
 def exact_poisson_tria(x: np.ndarray, y: np.ndarray) -> np.ndarray:
     """Analytic Laplace solution left in the comments of triapoissonparallelimpl1.F:954-955."""
     return (np.cosh(np.pi * y) - np.sinh(np.pi * y) / np.tanh(np.pi)) * np.sin(np.pi * x)
