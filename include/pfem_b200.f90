@@ -10,6 +10,7 @@
 !
 ! NOTE: no Fortran compiler exists in the build image, so this file is kept deliberately thin (pure interface
 ! blocks + one-line wrappers, names mirrored 1:1 from include/pfem_b200.h) and has not been compiled here.
+! Whoever has a toolchain: `gfortran -std=f2008 -fsyntax-only include/pfem_b200.f90` is the first check (INTEGRATION.md).
       MODULE Module_SolverB200
       USE, INTRINSIC :: ISO_C_BINDING
       IMPLICIT NONE
@@ -17,6 +18,8 @@
       INTEGER, PARAMETER :: PFEM_POISSON_TRIA=0, PFEM_POISSON_TETRA=1
       INTEGER, PARAMETER :: PFEM_ELASTICITY_TRIA=2, PFEM_ELASTICITY_TETRA=3
       INTEGER, PARAMETER :: PFEM_PC_NONE=0, PFEM_PC_JACOBI=1
+      INTEGER, PARAMETER :: PFEM_PC_BJACOBI_ILU0=2     ! the default, like solverpetsc.F:206 PCSetType(PCBJACOBI)
+      INTEGER, PARAMETER :: PFEM_ERR_PATTERN=8         ! slow-path add outside the pattern (never dropped silently)
 
       INTERFACE
         INTEGER(C_INT) FUNCTION pfem_comm_unique_id(id128) BIND(C)
@@ -39,6 +42,11 @@
           IMPORT; TYPE(C_PTR), VALUE :: h
           REAL(C_DOUBLE), VALUE :: rtol, abstol, dtol
           INTEGER(C_INT), VALUE :: max_it, pc_type
+        END FUNCTION
+        ! PetscInitialize(..., "petsc_options.dat") + KSPSetFromOptions/PCSetFromOptions; path is NUL-terminated
+        INTEGER(C_INT) FUNCTION pfem_solver_set_options_from_file(h, path) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: h
+          CHARACTER(KIND=C_CHAR) :: path(*)
         END FUNCTION
         INTEGER(C_INT) FUNCTION pfem_solver_set_mesh(h, kind, nElem, conn, nNode, coords, node_map_get_old) BIND(C)
           IMPORT; TYPE(C_PTR), VALUE :: h
@@ -138,6 +146,56 @@
         INTEGER(C_INT) FUNCTION pfem_elasticity_tetra_ke(x, y, z, elemData, timeData, valC, valDotC, K, F) BIND(C)
           IMPORT; REAL(C_DOUBLE) :: x(4), y(4), z(4), elemData(*), timeData(*), valC(12), valDotC(12), K(12,12), F(12)
         END FUNCTION
+        ! explicit dynamics: elementutilitieselasticity2D.F:158,283; elasticity3D.F:575,401; triaelasticityexplicit.F:881-1121
+        INTEGER(C_INT) FUNCTION pfem_residual_elasticity_linear_tria(x, y, elemData, timeData, dispC, veloC, Flocal) BIND(C)
+          IMPORT; REAL(C_DOUBLE) :: x(3), y(3), elemData(*), timeData(*), dispC(6), veloC(6), Flocal(6)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_mass_matrix_linear_tria(x, y, elemData, Mlocal) BIND(C)
+          IMPORT; REAL(C_DOUBLE) :: x(3), y(3), elemData(*), Mlocal(6)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_residual_elasticity_linear_tetra(x, y, z, elemData, timeData, valC, valDotC, Flocal) BIND(C)
+          IMPORT; REAL(C_DOUBLE) :: x(4), y(4), z(4), elemData(*), timeData(*), valC(12), valDotC(12), Flocal(12)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_mass_matrix_linear_tetra(x, y, z, elemData, Mlocal) BIND(C)
+          IMPORT; REAL(C_DOUBLE) :: x(4), y(4), z(4), elemData(*), Mlocal(12)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_create(ex, device) BIND(C)
+          IMPORT; TYPE(C_PTR) :: ex
+          INTEGER(C_INT), VALUE :: device
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_free(ex) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_set_mesh(ex, kind, nElem, conn, nNode, coords) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+          INTEGER(C_INT), VALUE :: kind, nElem, nNode
+          INTEGER(C_INT) :: conn(nElem,*)
+          REAL(C_DOUBLE) :: coords(nNode,*)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_set_free_dofs(ex, size_global, assyForSoln) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+          INTEGER(C_INT), VALUE :: size_global
+          INTEGER(C_INT) :: assyForSoln(*)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_lumped_mass(ex, elemData) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+          REAL(C_DOUBLE) :: elemData(*)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_advance(ex, nsteps, dt, elemData, timeData) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+          INTEGER(C_INT), VALUE :: nsteps
+          REAL(C_DOUBLE), VALUE :: dt
+          REAL(C_DOUBLE) :: elemData(*), timeData(*)
+        END FUNCTION
+        ! disp / dispPrev2 / velo / acce / mass: node-slot arrays (nNode*ndof), like the driver's plain arrays
+        INTEGER(C_INT) FUNCTION pfem_explicit_get_state(ex, disp, dispPrev2, velo, acce, mass) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+          REAL(C_DOUBLE) :: disp(*), dispPrev2(*), velo(*), acce(*), mass(*)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION pfem_explicit_set_state(ex, disp, dispPrev2) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: ex
+          REAL(C_DOUBLE) :: disp(*), dispPrev2(*)
+        END FUNCTION
       END INTERFACE
 
       TYPE B200Solver
@@ -145,6 +203,7 @@
         INTEGER :: ierr = 0
       CONTAINS
         PROCEDURE :: create
+        PROCEDURE :: setOptionsFromFile
         PROCEDURE :: initialise
         PROCEDURE :: setZero
         PROCEDURE :: free
@@ -169,12 +228,26 @@
         END IF
       END SUBROUTINE check
 
+      ! id128: the 128-byte communicator id of rank 0 (pfem_comm_unique_id, broadcast by the driver); not needed for nranks = 1
       SUBROUTINE create(this, device, rank, nranks, id128)
         CLASS(B200Solver) :: this
         INTEGER, INTENT(IN) :: device, rank, nranks
-        CHARACTER(KIND=C_CHAR) :: id128(128)
-        call check(pfem_solver_create(this%h, device, rank, nranks, id128), "create")
+        CHARACTER(KIND=C_CHAR), OPTIONAL :: id128(128)
+        CHARACTER(KIND=C_CHAR) :: none(128)
+        IF (PRESENT(id128)) THEN
+          call check(pfem_solver_create(this%h, device, rank, nranks, id128), "create")
+        ELSE
+          none = C_NULL_CHAR
+          call check(pfem_solver_create(this%h, device, rank, nranks, none), "create")
+        END IF
       END SUBROUTINE create
+
+      ! after initialise: the options file PetscInitialize would read (tetrapoissonparallelimpl1.F:168)
+      SUBROUTINE setOptionsFromFile(this, path)
+        CLASS(B200Solver) :: this
+        CHARACTER(LEN=*), INTENT(IN) :: path
+        call check(pfem_solver_set_options_from_file(this%h, TRIM(path)//C_NULL_CHAR), "setOptionsFromFile")
+      END SUBROUTINE setOptionsFromFile
 
       SUBROUTINE initialise(this, size_local, size_global, diag_nnz, offdiag_nnz)
         CLASS(B200Solver) :: this

@@ -899,14 +899,15 @@ static int grid_for(pfem_solver *h, long long work_items, int per_thread);
 __global__ void __launch_bounds__(ILU_WARPS * 32)
 ilu_factor_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ dlo, const int *__restrict__ ddiag,
                   const int *__restrict__ dhi, double *fval, double *invd, unsigned int *ready, unsigned int epoch,
-                  unsigned long long *ticket, unsigned long long ticket_base, CgState *st)
+                  unsigned long long *ticket, unsigned long long ticket_base, CgState *st, const int *__restrict__ order)
 {
     __shared__ unsigned long long s_blk;
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int i = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
-    if (i >= nloc) return;
+    const int slot = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    if (slot >= nloc) return;
+    const int i = order[slot];             // rows in level order: a row's dependencies sit earlier in the ticket order
     const int q0 = dlo[i], qd = ddiag[i], q1 = dhi[i];
     int fail = 0;
     for (int q = q0; q < qd; q++) {
@@ -946,15 +947,16 @@ ilu_factor_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *
 __global__ void __launch_bounds__(ILU_WARPS * 32)
 ilu_lower_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ dlo, const int *__restrict__ ddiag,
                  const double *__restrict__ fval, const double *__restrict__ r, IluTagged *y, unsigned long long tag,
-                 unsigned long long *ticket, unsigned long long ticket_base, CgState *st)
+                 unsigned long long *ticket, unsigned long long ticket_base, CgState *st, const int *__restrict__ order)
 {
     __shared__ unsigned long long s_blk;
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
     __syncthreads();
     if (st->reason != 0) return;
     const int lane = threadIdx.x & 31;
-    const int i = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
-    if (i >= nloc) return;
+    const int slot = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    if (slot >= nloc) return;
+    const int i = order[slot];
     const int q0 = dlo[i], qd = ddiag[i];
     double sum = r[i];
     int fail = 0;
@@ -974,16 +976,16 @@ __global__ void __launch_bounds__(ILU_WARPS * 32)
 ilu_upper_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ ddiag, const int *__restrict__ dhi,
                  const double *__restrict__ fval, const double *__restrict__ invd, const IluTagged *__restrict__ y,
                  IluTagged *zt, double *__restrict__ z, unsigned long long tag, unsigned long long *ticket,
-                 unsigned long long ticket_base, CgState *st)
+                 unsigned long long ticket_base, CgState *st, const int *__restrict__ order)
 {
     __shared__ unsigned long long s_blk;
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
     __syncthreads();
     if (st->reason != 0) return;
     const int lane = threadIdx.x & 31;
-    const long long ii = (long long)nloc - 1 - ((long long)s_blk * ILU_WARPS + (threadIdx.x >> 5));
-    if (ii < 0) return;
-    const int i = (int)ii;
+    const int slot = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    if (slot >= nloc) return;
+    const int i = order[slot];             // backward levels: rows whose upper entries are all solved come first
     const int q0 = ddiag[i] + 1, q1 = dhi[i];
     double sum = y[i].v;                           // written by the forward kernel (kernel boundary)
     int fail = 0;
@@ -1002,6 +1004,76 @@ ilu_upper_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *_
     }
 }
 
+__global__ void ilu_iota_kernel(int n, int *__restrict__ v)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+// ---- level schedule (symbolic, once per pattern) ----------------------------------------------------------------------
+// In natural order consecutive rows depend on each other (x-neighbours), so warps taken in row order spend their time
+// polling: 60 ms per triangular solve on 1 M rows.  Rows are therefore handed out in LEVEL order (level = longest
+// dependency chain below the row; a stable sort by level): the rows in flight are then mutually independent and a
+// dependency is almost always already there when a warp asks for it.  Levels by chaotic relaxation (monotone, converges in
+// at most #levels sweeps, far fewer in practice), rows sorted by a stable radix sort.  The numerical result does not
+// depend on the order (each row is summed by one warp in ascending column order).
+__global__ void ilu_level_sweep_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *__restrict__ lo_arr,
+                                       const int *__restrict__ hi_arr, int upper, int *level, int *__restrict__ changed)
+{
+    bool any = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += gridDim.x * blockDim.x) {
+        // lower: entries [dlo, ddiag)   upper: entries (ddiag, dhi)
+        const int a = upper ? lo_arr[i] + 1 : lo_arr[i], b = hi_arr[i];
+        int lv = 0;
+        for (int q = a; q < b; q++) lv = max(lv, 1 + __ldcg(level + (col[q] - row_lo)));
+        if (lv > level[i]) { level[i] = lv; any = true; }
+    }
+    if (any) *changed = 1;
+}
+
+static int ilu_schedule(pfem_solver *h)
+{
+    if (h->ilu_sched_seq == h->pattern_seq && h->ilu_order_l.p) return PFEM_OK;
+    cudaStream_t s = h->stream;
+    const int nloc = h->size_local;
+    const size_t n1 = (size_t)(nloc > 0 ? nloc : 1);
+    PFEM_TRY(h->ilu_order_l.alloc(n1)); PFEM_TRY(h->ilu_order_u.alloc(n1));
+    if (nloc == 0) { h->ilu_sched_seq = h->pattern_seq; return PFEM_OK; }
+    DevBuf<int> level, level_s, rows, changed;
+    PFEM_TRY(level.alloc(n1)); PFEM_TRY(level_s.alloc(n1)); PFEM_TRY(rows.alloc(n1)); PFEM_TRY(changed.alloc(1));
+    for (int upper = 0; upper < 2; upper++) {
+        PFEM_CUDA(cudaMemsetAsync(level.p, 0, n1 * sizeof(int), s));
+        int sweeps = 0;
+        while (true) {
+            PFEM_CUDA(cudaMemsetAsync(changed.p, 0, sizeof(int), s));
+            for (int k = 0; k < 8; k++)
+                ilu_level_sweep_kernel<<<grid_for(h, nloc, 1), CG_THREADS, 0, s>>>(nloc, h->row_lo, h->col.p, upper ? h->ilu_ddiag.p : h->ilu_dlo.p,
+                                                                                 upper ? h->ilu_dhi.p : h->ilu_ddiag.p, upper, level.p, changed.p);
+            h->launches += 8;
+            sweeps += 8;
+            int ch = 0;
+            PFEM_CUDA(cudaMemcpyAsync(&ch, changed.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            PFEM_CUDA(cudaStreamSynchronize(s));
+            if (!ch) break;
+            if (sweeps > nloc + 16) { set_error("ILU(0): level schedule did not converge"); return PFEM_ERR_STATE; }
+        }
+        // stable sort of the rows by level
+        ilu_iota_kernel<<<grid_for(h, nloc, 1), CG_THREADS, 0, s>>>(nloc, rows.p);
+        size_t bytes = 0;
+        int *out = upper ? h->ilu_order_u.p : h->ilu_order_l.p;
+        PFEM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, level.p, level_s.p, rows.p, out, nloc, 0, 32, s));
+        DevBuf<char> tmp;
+        PFEM_TRY(tmp.alloc(bytes));
+        PFEM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, level.p, level_s.p, rows.p, out, nloc, 0, 32, s));
+        int maxlev = 0;
+        PFEM_CUDA(cudaMemcpyAsync(&maxlev, level_s.p + nloc - 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PFEM_CUDA(cudaStreamSynchronize(s));
+        (upper ? h->ilu_levels_u : h->ilu_levels_l) = maxlev + 1;
+        h->launches += 2;
+    }
+    h->ilu_sched_seq = h->pattern_seq;
+    return PFEM_OK;
+}
+
 // z = M^-1 r with M = ILU(0) of the diagonal block: two launches
 static int ilu_apply(pfem_solver *h)
 {
@@ -1013,10 +1085,10 @@ static int ilu_apply(pfem_solver *h)
     unsigned long long *ticket = reinterpret_cast<unsigned long long *>(h->ilu_ticket.p);
     const unsigned long long tag = ++h->ilu_tag;
     ilu_lower_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_dlo.p, h->ilu_ddiag.p, h->ilu_fval.p, h->r.p, y, tag,
-                                                     ticket, h->ilu_tickets, h->cg.p);
+                                                     ticket, h->ilu_tickets, h->cg.p, h->ilu_order_l.p);
     h->ilu_tickets += nblk;
     ilu_upper_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_ddiag.p, h->ilu_dhi.p, h->ilu_fval.p, h->ilu_invd.p, y, zt,
-                                                     h->z.p, tag, ticket, h->ilu_tickets, h->cg.p);
+                                                     h->z.p, tag, ticket, h->ilu_tickets, h->cg.p, h->ilu_order_u.p);
     h->ilu_tickets += nblk;
     h->launches += 2;
     return PFEM_OK;
@@ -1052,10 +1124,12 @@ static int ilu_setup(pfem_solver *h)
     PFEM_CUDA(cudaMemcpyAsync(h->ilu_fval.p, h->val.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToDevice, s));
     PFEM_CUDA(cudaStreamSynchronize(s));
     if (nbad) { set_error("ILU(0): %d rows of the diagonal block have no diagonal entry", nbad); return PFEM_ERR_STATE; }
+    PFEM_TRY(ilu_schedule(h));           // symbolic part: once per pattern
     const unsigned int nblk = (unsigned int)((nloc + ILU_WARPS - 1) / ILU_WARPS);
     ilu_factor_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_dlo.p, h->ilu_ddiag.p, h->ilu_dhi.p, h->ilu_fval.p,
                                                       h->ilu_invd.p, h->ilu_ready.p, ++h->ilu_epoch,
-                                                      reinterpret_cast<unsigned long long *>(h->ilu_ticket.p), h->ilu_tickets, h->cg.p);
+                                                      reinterpret_cast<unsigned long long *>(h->ilu_ticket.p), h->ilu_tickets, h->cg.p,
+                                                      h->ilu_order_l.p);
     h->ilu_tickets += nblk;
     h->launches += 2;
     return PFEM_OK;

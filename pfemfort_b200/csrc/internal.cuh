@@ -174,7 +174,9 @@ struct pfem_solver {
     pfem::DevBuf<int> brow_ids, brow_ptr, bcol;   // boundary row ids (local), ptr, compact ghost index
     pfem::DevBuf<int> off_ptr;                    // [size_local+1] per-row pointer into bcol/bval (persistent CG kernel)
     // PCBJACOBI/ILU(0): diagonal-block row ranges, factor values, inverted pivots, tagged solve vectors, row-ready epochs
-    pfem::DevBuf<int> ilu_dlo, ilu_ddiag, ilu_dhi;
+    pfem::DevBuf<int> ilu_dlo, ilu_ddiag, ilu_dhi, ilu_order_l, ilu_order_u;   // order_*: rows sorted by dependency level
+    long long pattern_seq = 0, ilu_sched_seq = -1;
+    int ilu_levels_l = 0, ilu_levels_u = 0;
     pfem::DevBuf<double> ilu_fval, ilu_invd, ilu_y, ilu_z, ilu_ticket;
     pfem::DevBuf<unsigned int> ilu_ready;
     unsigned long long ilu_tickets = 0, ilu_tag = 0;

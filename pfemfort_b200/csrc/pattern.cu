@@ -471,6 +471,7 @@ int build_pattern(pfem_solver *h, int nElem, int nsize, const int *elemDof, cons
     }
     h->values_zero = true;
     h->rhs_zero = true;
+    h->pattern_seq++;                  // structures derived from the pattern (ILU level schedule) are stale
     PFEM_TRY(h->neg_count.alloc(1));
     // the value-pass streams (row kernels: build_asm_streams + plan_assembly; tile kernel: build_ctiles) are built on
     // first use by assemble_values, for the kernel that actually runs

@@ -16,7 +16,7 @@ NAMES = {0: "iteration top", 1: "direction loop done", 2: "  CTA barrier #1", 3:
          13: "  red + poll", 14: "  acquire fence", 15: "  partial sums (+ mailbox) done", 16: "scalar step done", 17: "CTA barrier #2 left",
          20: "update loop done", 21: "  CTA barrier #1", 22: "  block sums + stcg + release fence", 23: "  red + poll", 24: "  acquire fence",
          25: "  partial sums (+ mailbox) done", 26: "scalar step done", 27: "CTA barrier #2 left"}
-for cells in [int(a) for a in sys.argv[1:]] or [16]:
+for cells in ([int(a) for a in sys.argv[1:]] or [16]) if __name__ == "__main__" else []:
     m = M.gen_tetra(-1, 1, cells, -1, 1, cells, -1, 1, cells)
     num = D.number(m, S.POISSON_TETRA)
     s = S.SolverB200(0)
