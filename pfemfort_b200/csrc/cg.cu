@@ -391,8 +391,8 @@ static int exclusive_scan(pfem_solver *h, const T *in, T *out, int n)
 {
     size_t bytes = 0;
     PFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream));
-    DevBuf<char> tmp;
-    PFEM_TRY(tmp.alloc(bytes));
+    Tmp<char> tmp;
+    PFEM_TRY(tmp.alloc(h, 18, bytes));
     PFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, h->stream));
     h->launches++;
     return PFEM_OK;
@@ -403,15 +403,15 @@ int build_solver_structures(pfem_solver *h)
     cudaStream_t s = h->stream;
     const int nloc = h->size_local, G = h->sm_count * 8;
     const int nslices = (nloc + 31) / 32, nrows_padded = nslices * 32;
-    DevBuf<int> ndiag, noff, flags, brow_rank;
+    Tmp<int> ndiag, noff, flags, brow_rank;          // temporaries live in the handle's persistent scratch (internal.cuh)
     DevBuf<int> &off_ptr = h->off_ptr;
-    DevBuf<long long> slice_sz;
-    PFEM_TRY(ndiag.alloc((size_t)nloc + 1));
-    PFEM_TRY(noff.alloc((size_t)nloc + 1));
+    Tmp<long long> slice_sz;
+    PFEM_TRY(ndiag.alloc(h, 8, (size_t)nloc + 1));
+    PFEM_TRY(noff.alloc(h, 9, (size_t)nloc + 1));
     PFEM_TRY(off_ptr.alloc((size_t)nloc + 1));
-    PFEM_TRY(flags.alloc((size_t)nloc + 1));
-    PFEM_TRY(brow_rank.alloc((size_t)nloc + 1));
-    PFEM_TRY(slice_sz.alloc((size_t)nslices + 1));
+    PFEM_TRY(flags.alloc(h, 10, (size_t)nloc + 1));
+    PFEM_TRY(brow_rank.alloc(h, 11, (size_t)nloc + 1));
+    PFEM_TRY(slice_sz.alloc(h, 12, (size_t)nslices + 1));
     PFEM_CUDA(cudaMemsetAsync(ndiag.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
     PFEM_CUDA(cudaMemsetAsync(noff.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
     PFEM_CUDA(cudaMemsetAsync(flags.p, 0, ((size_t)nloc + 1) * sizeof(int), s));
@@ -442,22 +442,22 @@ int build_solver_structures(pfem_solver *h)
     PFEM_TRY(h->brow_ids.alloc((size_t)n_brows + 1));
     PFEM_TRY(h->brow_ptr.alloc((size_t)n_brows + 1));
     // ghost list = sorted unique off-diagonal global columns (PETSc's garray)
-    DevBuf<int> ghost;
+    Tmp<int> ghost;
     h->ghost_cols.clear();
     h->n_ghost = 0;
     if (nnz_off > 0) {
-        DevBuf<int> oc, oc_sorted, nsel;
-        PFEM_TRY(oc.alloc((size_t)nnz_off));
-        PFEM_TRY(oc_sorted.alloc((size_t)nnz_off));
-        PFEM_TRY(ghost.alloc((size_t)nnz_off));
-        PFEM_TRY(nsel.alloc(1));
+        Tmp<int> oc, oc_sorted, nsel;
+        PFEM_TRY(oc.alloc(h, 13, (size_t)nnz_off));
+        PFEM_TRY(oc_sorted.alloc(h, 14, (size_t)nnz_off));
+        PFEM_TRY(ghost.alloc(h, 15, (size_t)nnz_off));
+        PFEM_TRY(nsel.alloc(h, 16, 1));
         gather_offdiag_cols_kernel<<<G, 256, 0, s>>>(nloc, h->row_lo, h->row_hi, h->rowptr.p, h->col.p, off_ptr.p, oc.p);
         h->launches++;
         size_t b1 = 0, b2 = 0;
         PFEM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, b1, oc.p, oc_sorted.p, nnz_off, 0, 32, s));
         PFEM_CUDA(cub::DeviceSelect::Unique(nullptr, b2, oc_sorted.p, ghost.p, nsel.p, nnz_off, s));
-        DevBuf<char> tmp;
-        PFEM_TRY(tmp.alloc(b1 > b2 ? b1 : b2));
+        Tmp<char> tmp;
+        PFEM_TRY(tmp.alloc(h, 17, b1 > b2 ? b1 : b2));
         PFEM_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, b1, oc.p, oc_sorted.p, nnz_off, 0, 32, s));
         PFEM_CUDA(cub::DeviceSelect::Unique(tmp.p, b2, oc_sorted.p, ghost.p, nsel.p, nnz_off, s));
         h->launches += 2;
@@ -468,7 +468,7 @@ int build_solver_structures(pfem_solver *h)
         h->ghost_cols.resize(ng);
         PFEM_CUDA(cudaMemcpy(h->ghost_cols.data(), ghost.p, (size_t)ng * sizeof(int), cudaMemcpyDeviceToHost));
     } else {
-        PFEM_TRY(ghost.alloc(1));
+        PFEM_TRY(ghost.alloc(h, 15, 1));
     }
     fill_structures_kernel<<<G, 256, 0, s>>>(nloc, nrows_padded, h->row_lo, h->row_hi, h->rowptr.p, h->col.p,
                                              h->A.slice_off.p, off_ptr.p, ghost.p, h->n_ghost, h->A.col.p, h->bcol.p,
@@ -893,6 +893,9 @@ __global__ void ilu_rows_kernel(int nloc, int row_lo, int row_hi, const int *__r
 }
 
 static constexpr int ILU_WARPS = 8;
+// rows per warp and ticket.  1 is the measured best: 8 rows per warp widens the window of slots in flight to ~25 levels and the
+// solves get 2.4x slower (tet100: 4.2 -> 10.2 ms per iteration); the solves are bound by #levels x per-level latency (~4 us)
+static constexpr int ILU_RPW = 1, ILU_CHUNK = ILU_WARPS * ILU_RPW;
 static int grid_for(pfem_solver *h, long long work_items, int per_thread);
 
 // numeric ILU(0) of the diagonal block, in place on fval (a copy of the CSR values); invd = inverted pivots
@@ -905,7 +908,9 @@ ilu_factor_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1ULL) - ticket_base;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int slot = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    // slots of one chunk are interleaved over the warps: a dependency has a lower slot => another warp, or this warp earlier
+    for (int k = 0; k < ILU_RPW; k++) {
+    const int slot = (int)s_blk * ILU_CHUNK + k * ILU_WARPS + (threadIdx.x >> 5);
     if (slot >= nloc) return;
     const int i = order[slot];             // rows in level order: a row's dependencies sit earlier in the ticket order
     const int q0 = dlo[i], qd = ddiag[i], q1 = dhi[i];
@@ -941,6 +946,8 @@ ilu_factor_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *
         __threadfence();
         st_release_gpu_u32(ready + i, epoch);
     }
+    __syncwarp();
+    }
 }
 
 // forward substitution  y_i = r_i - sum_{j in L(i)} l_ij y_j   (ascending j)
@@ -954,7 +961,8 @@ ilu_lower_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *_
     __syncthreads();
     if (st->reason != 0) return;
     const int lane = threadIdx.x & 31;
-    const int slot = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    for (int k = 0; k < ILU_RPW; k++) {
+    const int slot = (int)s_blk * ILU_CHUNK + k * ILU_WARPS + (threadIdx.x >> 5);
     if (slot >= nloc) return;
     const int i = order[slot];
     const int q0 = dlo[i], qd = ddiag[i];
@@ -969,6 +977,7 @@ ilu_lower_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *_
     }
     if (__any_sync(0xffffffffu, fail) && lane == 0) st->reason = -101;
     if (lane == 0) st_tagged_gpu(y + i, sum, tag);
+    }
 }
 
 // backward substitution  z_i = (y_i - sum_{j in U(i), j > i} u_ij z_j) * (1/u_ii)   (ascending j), rows in descending order
@@ -983,7 +992,8 @@ ilu_upper_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *_
     __syncthreads();
     if (st->reason != 0) return;
     const int lane = threadIdx.x & 31;
-    const int slot = (int)s_blk * ILU_WARPS + (threadIdx.x >> 5);
+    for (int k = 0; k < ILU_RPW; k++) {
+    const int slot = (int)s_blk * ILU_CHUNK + k * ILU_WARPS + (threadIdx.x >> 5);
     if (slot >= nloc) return;
     const int i = order[slot];             // backward levels: rows whose upper entries are all solved come first
     const int q0 = ddiag[i] + 1, q1 = dhi[i];
@@ -1001,6 +1011,7 @@ ilu_upper_kernel(int nloc, int row_lo, const int *__restrict__ col, const int *_
         const double zi = __dmul_rn(sum, invd[i]);
         st_tagged_gpu(zt + i, zi, tag);
         z[i] = zi;
+    }
     }
 }
 
@@ -1079,7 +1090,7 @@ static int ilu_apply(pfem_solver *h)
 {
     cudaStream_t s = h->stream;
     const int nloc = h->size_local;
-    const unsigned int nblk = (unsigned int)((nloc + ILU_WARPS - 1) / ILU_WARPS);
+    const unsigned int nblk = (unsigned int)((nloc + ILU_CHUNK - 1) / ILU_CHUNK);
     if (nblk == 0) return PFEM_OK;
     IluTagged *y = reinterpret_cast<IluTagged *>(h->ilu_y.p), *zt = reinterpret_cast<IluTagged *>(h->ilu_z.p);
     unsigned long long *ticket = reinterpret_cast<unsigned long long *>(h->ilu_ticket.p);
@@ -1125,7 +1136,7 @@ static int ilu_setup(pfem_solver *h)
     PFEM_CUDA(cudaStreamSynchronize(s));
     if (nbad) { set_error("ILU(0): %d rows of the diagonal block have no diagonal entry", nbad); return PFEM_ERR_STATE; }
     PFEM_TRY(ilu_schedule(h));           // symbolic part: once per pattern
-    const unsigned int nblk = (unsigned int)((nloc + ILU_WARPS - 1) / ILU_WARPS);
+    const unsigned int nblk = (unsigned int)((nloc + ILU_CHUNK - 1) / ILU_CHUNK);
     ilu_factor_kernel<<<nblk, ILU_WARPS * 32, 0, s>>>(nloc, h->row_lo, h->col.p, h->ilu_dlo.p, h->ilu_ddiag.p, h->ilu_dhi.p, h->ilu_fval.p,
                                                       h->ilu_invd.p, h->ilu_ready.p, ++h->ilu_epoch,
                                                       reinterpret_cast<unsigned long long *>(h->ilu_ticket.p), h->ilu_tickets, h->cg.p,

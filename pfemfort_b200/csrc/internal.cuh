@@ -155,7 +155,9 @@ struct pfem_solver {
     pfem::DevBuf<int> t_desc, t_rows, t_el, t_inc, t_crec, t_ts2;
     pfem::DevBuf<unsigned char> t_cnt;
     pfem::DevBuf<long long> t_slice_off;
-    pfem::DevBuf<char> scratch[8];         // persistent set-up scratch (sort buffers, upload staging), re-used across calls
+    pfem::DevBuf<char> scratch[32];        // persistent, grow-only set-up scratch (sort buffers, upload staging, every temporary of the
+                                           // pattern pass): a cudaMalloc/cudaFree pair costs ~0.1 ms per MB when the driver really maps
+                                           // and unmaps, which made set_pattern bimodal (33 vs 80-110 ms on C5) while its temporaries were locals
     // colour-scheduled tile value pass (default for one dof per node): assembly_ctile.cu / .cuh
     bool ct_ready = false, ct_tried = false, rows_ready = false, ct_full = true;
     int asm_mode_req = 0;                  // 0 auto (tile kernel when it applies), 1 row kernels (bit-identical to the sequential order)
@@ -271,6 +273,12 @@ template <typename T> inline int scratch_get(pfem_solver *h, int idx, size_t cou
     *out = reinterpret_cast<T *>(h->scratch[idx].p);
     return PFEM_OK;
 }
+
+// set-up temporary in slot `slot` of the handle's persistent scratch: same use as a local DevBuf<T>, no allocation per call
+template <typename T> struct Tmp {
+    T *p = nullptr;
+    int alloc(pfem_solver *h, int slot, size_t count) { return scratch_get<T>(h, slot, count, &p); }
+};
 
 // PFEM_TRACE=1: print host wall time of the set-up stages (stderr)
 struct StageTimer {

@@ -1,5 +1,13 @@
-# r02 session 2, call 19 (8 GPUs): C5 and C4 at 8 GPUs (the driver's SCALE run repeats C5; this is the builder's own check)
+# r02 session 2, call 22 (1 GPU): pattern-pass temporaries in persistent scratch: full suite, PC comparison, bench (twice: e2e stability)
 mkdir -p gpurun_out
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 8 --steps 3 --warmup 3 --e2e-steps 1 --workload $2 --no-cpu-baseline; }
-timeout 600 bash -c "$(declare -f run); run 29741 c5" > gpurun_out/c19_c5_8gpu.log 2>&1; echo c5 rc=$?; tail -1 gpurun_out/c19_c5_8gpu.log | cut -c1-300
-timeout 400 bash -c "$(declare -f run); run 29742 c4" > gpurun_out/c19_c4_8gpu.log 2>&1; echo c4 rc=$?; tail -1 gpurun_out/c19_c4_8gpu.log | cut -c1-300
+( time timeout 600 python -m pytest tests/ -x -q -m gpu ) > gpurun_out/h_pytest_full.log 2>&1; echo pytest rc=$?; tail -4 gpurun_out/h_pytest_full.log | head -2
+timeout 120 python tools/pc_compare.py 40 100 > gpurun_out/h_pc_compare.log 2>&1; cat gpurun_out/h_pc_compare.log | cut -c1-200
+timeout 400 python bench.py > gpurun_out/h_bench_c5_1gpu.log 2>&1; echo bench rc=$?; tail -1 gpurun_out/h_bench_c5_1gpu.log | cut -c1-200
+timeout 300 python bench.py --no-cpu-baseline --no-parity --e2e-steps 4 --steps 3 > gpurun_out/h_bench_c5_1gpu_b.log 2>&1; echo bench2 rc=$?
+python - <<'PY'
+import json
+for f in ('h_bench_c5_1gpu', 'h_bench_c5_1gpu_b'):
+    l=[x for x in open(f'gpurun_out/{f}.log') if x.startswith('{"metric')]
+    if l:
+        d=json.loads(l[-1]); print(f, 'value %.4g' % d['value'], 'e2e ms %.1f' % d['e2e']['ms_per_step'], {k: round(v, 1) for k, v in d['e2e']['stage_ms'].items()})
+PY
