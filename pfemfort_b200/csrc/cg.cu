@@ -1500,7 +1500,21 @@ cg_persistent_kernel(const PcgArgs a, double *__restrict__ pbuf2)
         };
         // ---- halo push (nranks > 1): boundary values straight into the neighbours' ghost buffers ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * (unsigned int)ls.iter + 1u);
-        if (a.multi && a.halo_tag) {
+        if (a.multi && a.halo_tag == 1) {
+            // The LAST warp of every CTA pushes (4 736 threads share the entries) and then collects the NVLink write
+            // acknowledgements right away with a system fence of its own.  The 2-GPU stage trace (profiles/
+            // r02_pcg_trace_2gpu_tet100.log) showed why: when the threads that pushed include lane 0 of warp 0, that lane's
+            // release fence at the END of the phase waits one NVLink round trip for the acknowledgements of stores issued
+            // 20 us earlier (6 500 instead of 2 000 cycles, on every rank, every iteration).
+            if ((threadIdx.x >> 5) == (blockDim.x >> 5) - 1) {
+                bool sent = false;
+                for (int i = blockIdx.x * 32 + lane; i < a.n_send; i += gridDim.x * 32) {
+                    st_ghost_tagged(a.send_dst_t[i], pval(a.send_idx[i]), htag);
+                    sent = true;
+                }
+                if (sent) __threadfence_system();
+            }
+        } else if (a.multi && a.halo_tag) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_ghost_tagged(a.send_dst_t[i], pval(a.send_idx[i]), htag);
             if (a.halo_tag == 2 && gtid < a.n_send) __threadfence_system();      // push the posted stores out now (senders only)
         } else if (a.multi) {
@@ -1712,7 +1726,16 @@ cg_persistent_sr_kernel(const PcgArgs a, double *__restrict__ sv)
         }
         // ---- halo push of z (nranks > 1) ----
         const unsigned long long htag = (ls.seq << 32) | (unsigned long long)(4u * round + 1u);
-        if (a.multi && a.halo_tag) {
+        if (a.multi && a.halo_tag == 1) {
+            if ((threadIdx.x >> 5) == (blockDim.x >> 5) - 1) {       // see cg_persistent_kernel
+                bool sent = false;
+                for (int i = blockIdx.x * 32 + lane; i < a.n_send; i += gridDim.x * 32) {
+                    st_ghost_tagged(a.send_dst_t[i], a.z[a.send_idx[i]], htag);
+                    sent = true;
+                }
+                if (sent) __threadfence_system();
+            }
+        } else if (a.multi && a.halo_tag) {
             for (int i = gtid; i < a.n_send; i += gthreads) st_ghost_tagged(a.send_dst_t[i], a.z[a.send_idx[i]], htag);
             if (a.halo_tag == 2 && gtid < a.n_send) __threadfence_system();
         } else if (a.multi) {
@@ -1884,7 +1907,8 @@ static int cg_solve_persistent(pfem_solver *h, bool &used)
         // halo flavour: tag-validated 16-byte entries (default) or values + per-neighbour flags (PFEM_PCG_HALO=flag)
         const char *henv = getenv("PFEM_PCG_HALO");
         a.halo_tag = (a.multi && h->send_dst_t.p && !(henv && strcmp(henv, "flag") == 0)) ? 1 : 0;
-        if (a.halo_tag && henv && strcmp(henv, "tagf") == 0) a.halo_tag = 2;      // + a system fence by the sending threads
+        if (a.halo_tag && henv && strcmp(henv, "tagf") == 0) a.halo_tag = 2;      // all threads push + a system fence by the senders
+        if (a.halo_tag && henv && strcmp(henv, "tagall") == 0) a.halo_tag = 3;    // all threads push, no fence (first tag version)
         a.ghost_t = h->ghost_buf.p + h->ghost_tag_off;
         a.send_dst_t = h->send_dst_t.p;
     }
