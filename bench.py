@@ -469,8 +469,9 @@ def main():
     cgit_gbs = cgit_b * its / t_solve / 1e9
 
     # FP64 pipe of the value pass (BASELINE.json north_star: "with the FP64 pipe reported for the element kernels"):
-    # FP64 instructions per element of the kernel that ran (counted from the committed SASS listing, profiles/sass_*.txt;
-    # the library reports the figure of its own build), peak = SMs x 64 FP64 lanes x the SM clock under load.
+    # FP64 instructions per (row, element) visit of the kernel that ran, as the library reports for its own build: the
+    # DYNAMIC count (ncu sm__inst_executed_pipe_fp64 / visits; the static SASS count of the loop body, which includes the rarely
+    # taken lifting branches, is in profiles/r02_sass_hot_kernels.txt), peak = SMs x 64 FP64 lanes x the SM clock under load.
     asm_fp64 = None
     asm_kernel = None
     try:
