@@ -233,12 +233,12 @@
         CLASS(B200Solver) :: this
         INTEGER, INTENT(IN) :: device, rank, nranks
         CHARACTER(KIND=C_CHAR), OPTIONAL :: id128(128)
-        CHARACTER(KIND=C_CHAR) :: none(128)
+        CHARACTER(KIND=C_CHAR) :: no_id(128)
         IF (PRESENT(id128)) THEN
           call check(pfem_solver_create(this%h, device, rank, nranks, id128), "create")
         ELSE
-          none = C_NULL_CHAR
-          call check(pfem_solver_create(this%h, device, rank, nranks, none), "create")
+          no_id = C_NULL_CHAR
+          call check(pfem_solver_create(this%h, device, rank, nranks, no_id), "create")
         END IF
       END SUBROUTINE create
 
