@@ -1,0 +1,208 @@
+"""The oracle and the product's host logic against GOLDEN VECTORS PRODUCED BY RUNNING THE REFERENCE'S OWN SOURCE
+(tests/golden/ref_*.npz, made by tests/golden/make_reference_vectors.py through oracle/refrun: the reference's Fortran
+executed statement by statement with Fortran's typing and rounding rules; PETSc / MPI / METIS mocked).
+
+This is what pins the oracle: element routines bit for bit; the four `*parallelimpl1` PROGRAMs end to
+end -- numbering (f1), ElemDofArray, pattern incl. explicit zeros (a10), MatSetValues / lifting / VecSetValues / ForceBC
+(a9, a12), solver options (a11) -- bit for bit on one rank, integers bit for bit and values to 1e-12 on P ranks (the
+reference's own P-rank sums depend on PETSc's stash arrival order).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from pfemfort_b200 import driver as D, mesh as M, solver as S
+import properties as P
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KINDS = [S.POISSON_TRIA, S.POISSON_TETRA, S.ELASTICITY_TRIA, S.ELASTICITY_TETRA]
+CASES = {  # name: (kind, swap_34, rank counts)
+    "tria20x20": (S.POISSON_TRIA, False, (1, 3)),
+    "tet10": (S.POISSON_TETRA, False, (1, 2, 4)),
+    "cookmembranetria32": (S.ELASTICITY_TRIA, False, (1, 2)),
+    "beam3Dtet6366": (S.ELASTICITY_TETRA, True, (1,)),
+}
+CASE_IDS = [(n, p) for n, spec in CASES.items() for p in spec[2]]
+
+
+@pytest.fixture(scope="module")
+def elements():
+    return np.load(os.path.join(GOLDEN, "ref_elements.npz"))
+
+
+def _driver(name, p):
+    return np.load(os.path.join(GOLDEN, f"ref_driver_{name}_p{p}.npz"))
+
+
+# ---- element routines ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_element_routines_equal_the_executed_reference(elements, kind):
+    g = elements
+    xyz, ed, td, vc = g[f"ke{kind}_xyz"], g[f"ke{kind}_ed"], g[f"ke{kind}_td"], g[f"ke{kind}_valc"]
+    n = xyz.shape[0]
+    assert n >= 64 and 0 < g[f"ke{kind}_neg"].sum() < n          # both outcomes are covered
+    for e in range(n):
+        K, F, rc = O.element_ke(kind, xyz[e, 0], xyz[e, 1], xyz[e, 2], ed[e], td[e], vc[e])
+        assert (rc != 0) == bool(g[f"ke{kind}_neg"][e])          # the reference STOPs exactly where the oracle flags
+        if rc == 0:
+            assert np.array_equal(K, g[f"ke{kind}_K"][e]), (kind, e)
+            assert np.array_equal(F, g[f"ke{kind}_F"][e]), (kind, e)
+
+
+@pytest.mark.parametrize("kind", [S.ELASTICITY_TRIA, S.ELASTICITY_TETRA])
+def test_oracle_explicit_routines_equal_the_executed_reference(elements, kind):
+    g = elements
+    xyz, ed, td, vc = g[f"ke{kind}_xyz"], g[f"ke{kind}_ed"], g[f"ke{kind}_td"], g[f"ke{kind}_valc"]
+    for e in range(xyz.shape[0]):
+        if g[f"ke{kind}_neg"][e]:
+            continue
+        F, rc = O.residual_elasticity(kind, xyz[e, 0], xyz[e, 1], xyz[e, 2], ed[e], td[e], vc[e])
+        Ml, rc2 = O.mass_matrix(kind, xyz[e, 0], xyz[e, 1], xyz[e, 2], ed[e])
+        assert rc == 0 and rc2 == 0
+        assert np.array_equal(F, g[f"res{kind}_F"][e]), (kind, e)
+        assert np.array_equal(Ml, g[f"mass{kind}_M"][e]), (kind, e)
+
+
+def test_shipped_3d_elasticity_text_stops_in_computeBasisFunctions3D(elements):
+    """the three 3-D elasticity routines pass ETYPE = 1 and the reference STOPs at
+    elementutilitiesbasisfuncs.F:469 -- the reason for the documented-intent decision (ETYPE = 4, one Gauss point)."""
+    assert list(elements["shipped_elasticity3d_stop_lines"]) == [469, 469, 469]
+
+
+# ---- drivers ---------------------------------------------------------------------------------------------------------
+
+def _mesh(name, input_dir):
+    kind, swap, _ = CASES[name]
+    return M.read_mesh(os.path.join(input_dir, name), swap_34=swap), kind
+
+
+def _oracle_system(m, kind, nparts, npid):
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    o = O.number_dofs(m.nNode, ndof, m.dbc_node, m.dbc_dof, m.dbc_val, nparts, npid)
+    conn_new = o["node_map_get_new"][m.conn - 1]
+    edof = O.elem_dof_array(conn_new, o["NodeDofArrayNew"])
+    rp, col = O.pattern(edof, o["size_global"])
+    val, rhs, nbad = O.assemble(kind, conn_new, m.coords, o["node_map_get_old"], edof, o["solnApplied"],
+                                D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, rp, col)
+    assert nbad == 0
+    if m.fbc_node.size:
+        O.add_force_bc(rhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, o["node_map_get_new"], o["NodeDofArrayNew"],
+                       o["size_global"])
+    return o, conn_new, edof, rp, col, val, rhs
+
+
+@pytest.mark.parametrize("name,p", CASE_IDS)
+def test_oracle_numbering_equals_the_executed_driver(input_dir, name, p):
+    g = _driver(name, p)
+    m, kind = _mesh(name, input_dir)
+    npid = g["node_proc_id"] if p > 1 else None
+    o, conn_new, edof, *_ = _oracle_system(m, kind, p, npid)
+    assert np.array_equal(o["node_map_get_old"], g["node_map_get_old"])
+    assert np.array_equal(o["node_map_get_new"], g["node_map_get_new"])
+    assert np.array_equal(o["NodeDofArrayNew"].T, g["NodeDofArrayNew"])          # reference layout (node, dof)
+    assert np.array_equal(edof.T, g["ElemDofArray"])                             # reference layout (elem, local dof)
+    assert np.array_equal(o["solnApplied"], g["solnApplied"])
+    info = g["part_info"]
+    for r in range(p):
+        assert [o["node_start"][r], o["node_end"][r], o["size_local"][r]] == [info[r, 0], info[r, 1], info[r, 4]]
+        if info[r, 4] > 0:
+            assert [o["row_start"][r], o["row_end"][r]] == [info[r, 2], info[r, 3]]
+    assert o["size_global"] == g["rowptr"].size - 1 == info[:, 4].sum()
+    # assyForSoln (:698-734): free dofs in new numbering, 1-based position (node-1)*ndof + dof
+    nda = g["NodeDofArrayNew"]
+    free = np.flatnonzero(nda.reshape(-1) != 0) + 1
+    assert np.array_equal(free, g["assyForSoln"])
+    # the product's host numbering (csrc/host_driver.cu) gives the same arrays
+    num = D.number(m, kind, p, npid)
+    assert np.array_equal(num.node_map_get_old, g["node_map_get_old"])
+    assert np.array_equal(num.NodeDofArrayNew.T, g["NodeDofArrayNew"])
+    assert np.array_equal(num.elemDof.T, g["ElemDofArray"])
+    assert np.array_equal(num.solnApplied, g["solnApplied"])
+    assert np.array_equal(num.part_info[:, [0, 1, 4]], info[:, [0, 1, 4]])
+
+
+@pytest.mark.parametrize("name,p", CASE_IDS)
+def test_oracle_system_equals_what_the_executed_driver_hands_to_petsc(input_dir, name, p):
+    g = _driver(name, p)
+    m, kind = _mesh(name, input_dir)
+    o, conn_new, edof, rp, col, val, rhs = _oracle_system(m, kind, p, g["node_proc_id"] if p > 1 else None)
+    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(col, g["col"])     # pattern incl. the explicit zeros
+    if p == 1:
+        assert np.array_equal(val, g["val"])                                     # bit for bit
+        assert np.array_equal(rhs, g["rhs"])
+    else:
+        # P ranks: every rank adds its own elements; rows of other ranks go through PETSc's stash, so the reference's
+        # own sums are in (local, then stashed-by-source-rank) order, not in global element order
+        assert P.values_within(g["rowptr"], val, g["val"], 1e-12)
+        assert P.vector_within(rhs, g["rhs"], 1e-12)
+
+
+@pytest.mark.parametrize("name,p", CASE_IDS)
+def test_solver_options_and_call_order_of_the_executed_wrapper(name, p):
+    """solverpetsc.F as executed: KSPCG + PCBJACOBI (:187, :206), the three Mat options, negative indices ignored in the
+    RHS, pattern pass -> setZero (assemble, zero) -> value pass -> solve."""
+    g = _driver(name, p)
+    assert list(g["ksp_type"]) == ["cg"] and list(g["pc_type"]) == ["bjacobi"]
+    opts = set(g["options"])
+    assert "VecSetOption:('VEC_IGNORE_NEGATIVE_INDICES', True)" in opts
+    assert "MatSetOption:('MAT_NEW_NONZERO_LOCATIONS', True)" in opts
+    assert "MatSetOption:('MAT_KEEP_NONZERO_PATTERN', True)" in opts
+    assert "MatSetOption:('MAT_NEW_NONZERO_ALLOCATION_ERR', False)" in opts
+    order = list(g["call_order"])
+    assert order.index("KSPSetType") < order.index("PCSetType") < order.index("KSPSolve")
+    assert order[0] == "PetscInitialize"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_solution_and_temp_dat_records(input_dir, name):
+    """temp.dat of the executed driver (its KSPSolve is a direct solve in the mock) against the oracle's CG with the
+    reference's default PC at a tight tolerance; the Poisson drivers' index columns are (ii, old node of assyForSoln(ii))."""
+    g = _driver(name, 1)
+    m, kind = _mesh(name, input_dir)
+    o, conn_new, edof, rp, col, val, rhs = _oracle_system(m, kind, 1, None)
+    x, its, reason, rnorm = O.cg_bjacobi_ilu0(rp, col, val, rhs, rtol=1e-13, max_it=50000)
+    assert reason > 0
+    ref = g["temp_dat_value"]
+    assert np.abs(x - ref).max() <= 1e-7 * np.abs(ref).max()
+    if "temp_dat_index" in g.files:
+        idx = g["temp_dat_index"]
+        assert np.array_equal(idx[:, 0], np.arange(1, idx.shape[0] + 1))
+        assert np.array_equal(idx[:, 1], g["node_map_get_old"][g["assyForSoln"] - 1])
+    # the nodal field handed to the VTK writer = applied values + solution, in OLD numbering
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    num = D.number(m, kind)
+    nodal = np.asarray(D.nodal_solution(num, ref)).reshape(ndof, -1)
+    assert np.array_equal(nodal.T.reshape(-1), g["vtk_soln"])                     # reference layout (node-1)*ndof + dof
+
+
+def test_shipped_beam_file_stops_with_negative_jacobian():
+    """as shipped, beam3Dtet6366 has a negative Jacobian under the reference's own basis functions; the executed
+    driver STOPs in StiffnessResidualElasticityLinearTetra (elementutilitieselasticity3D.F:321)."""
+    assert list(_driver("beam3Dtet6366", 1)["shipped_stop_line"]) == [321]
+
+
+# ---- the generator still reproduces the committed files (build container only) --------------------------------------
+
+def _reference_present():
+    from oracle.refrun import run_reference as R
+    return R.available()
+
+
+@pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
+def test_regenerated_vectors_equal_the_committed_files(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(GOLDEN, "make_reference_vectors.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    new = gen.make_elements(str(tmp_path / "e.npz"))
+    old = np.load(os.path.join(GOLDEN, "ref_elements.npz"))
+    assert set(new) == set(old.files)
+    for k in old.files:
+        assert np.array_equal(new[k], old[k]), k
+    for tag, data in gen.make_drivers(None, only={"tria20x20_p3", "tet10_p2"}).items():
+        old = np.load(os.path.join(GOLDEN, f"ref_driver_{tag}.npz"))
+        for k in old.files:
+            assert np.array_equal(np.asarray(data[k]), old[k]), (tag, k)
