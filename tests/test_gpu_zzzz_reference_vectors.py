@@ -1,0 +1,106 @@
+"""The CUDA path (through the C ABI) against GOLDEN VECTORS PRODUCED BY RUNNING THE REFERENCE'S OWN SOURCE
+(tests/golden/ref_*.npz; see tests/golden/make_reference_vectors.py and tests/test_reference_vectors.py, which holds the
+oracle to the same files on the CPU).  Default arithmetic mode (reference order, no FMA): bit for bit.  Nothing here reads
+/root/reference or the oracle: the committed files are the reference's outputs."""
+import os
+
+import numpy as np
+import pytest
+
+from pfemfort_b200 import driver as D, explicit as X, mesh as M, solver as S
+from properties import values_within, vector_within
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KINDS = [S.POISSON_TRIA, S.POISSON_TETRA, S.ELASTICITY_TRIA, S.ELASTICITY_TETRA]
+CASES = {"tria20x20": (S.POISSON_TRIA, False), "tet10": (S.POISSON_TETRA, False),
+         "cookmembranetria32": (S.ELASTICITY_TRIA, False), "beam3Dtet6366": (S.ELASTICITY_TETRA, True)}
+
+
+@pytest.fixture(autouse=True)
+def default_mode(monkeypatch):
+    monkeypatch.delenv("PFEM_ASM", raising=False)
+
+
+@pytest.fixture(scope="module")
+def elements():
+    return np.load(os.path.join(GOLDEN, "ref_elements.npz"))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cuda_element_routines_equal_the_executed_reference(gpu, elements, kind):
+    g = elements
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    xyz, ed, td, vc = g[f"ke{kind}_xyz"], g[f"ke{kind}_ed"], g[f"ke{kind}_td"], g[f"ke{kind}_valc"]
+    n = xyz.shape[0]
+    checked = 0
+    for e in range(n):      # elemData / timeData differ per element in the golden set: one launch per element
+        K, F, neg = S.element_ke_batch(kind, xyz[e, 0][:, None], xyz[e, 1][:, None],
+                                       xyz[e, 2][:, None] if ndim == 3 else None, list(ed[e]), list(td[e]), vc[e][:, None])
+        assert bool(neg[0]) == bool(g[f"ke{kind}_neg"][e])        # PFEM_ERR_NEG_JACOBIAN exactly where the reference STOPs
+        if neg[0]:
+            continue
+        assert np.array_equal(K[:, :, 0], g[f"ke{kind}_K"][e]), (kind, e)
+        assert np.array_equal(F[:, 0], g[f"ke{kind}_F"][e]), (kind, e)
+        checked += 1
+    assert checked > n // 3
+
+
+@pytest.mark.parametrize("kind", [S.ELASTICITY_TRIA, S.ELASTICITY_TETRA])
+def test_cuda_explicit_routines_equal_the_executed_reference(gpu, elements, kind):
+    g = elements
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    xyz, ed, td, vc = g[f"ke{kind}_xyz"], g[f"ke{kind}_ed"], g[f"ke{kind}_td"], g[f"ke{kind}_valc"]
+    for e in range(xyz.shape[0]):
+        if g[f"ke{kind}_neg"][e]:
+            continue
+        z = xyz[e, 2] if ndim == 3 else None
+        assert np.array_equal(X.residual_elasticity(kind, xyz[e, 0], xyz[e, 1], z, list(ed[e]), list(td[e]), vc[e]),
+                              g[f"res{kind}_F"][e]), (kind, e)
+        assert np.array_equal(X.mass_matrix(kind, xyz[e, 0], xyz[e, 1], z, list(ed[e])), g[f"mass{kind}_M"][e]), (kind, e)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_system_equals_what_the_executed_driver_hands_to_petsc(gpu, input_dir, name):
+    """One rank: numbering on the GPU, pattern, value pass with lifting, ForceBC -- the matrix and right-hand side the
+    reference's PROGRAM hands to KSPSolve, bit for bit; the solution against the reference run's (direct) solve."""
+    kind, swap = CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"ref_driver_{name}_p1.npz"))
+    m = M.read_mesh(os.path.join(input_dir, name), swap_34=swap)
+    num = D.number(m, kind, on_gpu=True)
+    assert np.array_equal(num.NodeDofArrayNew.T, g["NodeDofArrayNew"]) and np.array_equal(num.elemDof.T, g["ElemDofArray"])
+    assert np.array_equal(num.solnApplied, g["solnApplied"])
+    s = S.SolverB200(0)
+    D.run_rank(s, m, num, rtol=1e-12, max_it=50000)
+    rp, col, val = s.get_csr()
+    rhs = s.get_rhs()
+    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(col, g["col"])
+    assert s.assembly_mode()[0] in (0, 1)
+    assert np.array_equal(val, g["val"]) and np.array_equal(rhs, g["rhs"])
+    x = s.get_solution()
+    ref = g["temp_dat_value"]                 # the mock KSPSolve is a direct solve; CG here stops at rtol 1e-12
+    assert np.abs(x - ref).max() <= 1e-5 * np.abs(ref).max()
+    s.free()
+
+
+@pytest.mark.parametrize("name,p", [("tria20x20", 3), ("tet10", 2), ("tet10", 4), ("cookmembranetria32", 2)])
+def test_cuda_numbering_equals_the_executed_p_rank_driver(gpu, input_dir, name, p):
+    """P simulated ranks of the reference: the GPU numbering block (csrc/gpu_setup.cu) with the reference run's node
+    partition, bit for bit -- renumbering, NodeDofArrayNew, ElemDofArray, applied values, per-rank node / row ranges,
+    assyForSoln.  (The P-rank matrix blocks are held to the oracle in tests/test_gpu_multi.py and the oracle to these files
+    in tests/test_reference_vectors.py.)"""
+    kind, swap = CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"ref_driver_{name}_p{p}.npz"))
+    m = M.read_mesh(os.path.join(input_dir, name), swap_34=swap)
+    num = D.number(m, kind, p, g["node_proc_id"], on_gpu=True)
+    assert np.array_equal(num.node_map_get_old, g["node_map_get_old"])
+    assert np.array_equal(num.node_map_get_new, g["node_map_get_new"])
+    assert np.array_equal(num.NodeDofArrayNew.T, g["NodeDofArrayNew"]) and np.array_equal(num.elemDof.T, g["ElemDofArray"])
+    assert np.array_equal(num.solnApplied, g["solnApplied"])
+    info = g["part_info"]
+    assert np.array_equal(num.part_info[:, [0, 1, 4]], info[:, [0, 1, 4]])
+    own = info[:, 4] > 0
+    assert np.array_equal(num.part_info[own][:, [2, 3]], info[own][:, [2, 3]])
+    lst, assy, edof = D.gpu_local_elements_and_assy(num, 0)
+    assert np.array_equal(assy, g["assyForSoln"])
