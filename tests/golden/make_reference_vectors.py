@@ -229,9 +229,41 @@ def make_drivers(outdir, only=None):
     return made
 
 
+# ---- the compiled mesh generator ----------------------------------------------------------------------------------------
+
+GENTETRA_GRIDS = {
+    # name: (x0, x1, nEx, y0, y1, nEy, z0, z1, nEz)
+    'tet10_fixture': (-2, 2, 10, -1, 1, 10, -1, 1, 10),
+    'defaults5': (-1.6, 1.6, 5, -1.6, 1.6, 5, -1.6, 1.6, 5),
+    'one_cell': (0, 1, 1, 0, 1, 1, 0, 1, 1),
+    'cube30': (-1, 1, 30, -1, 1, 30, -1, 1, 30),
+    'beam': (-0.5, 0.5, 6, 0.0, 6.0, 36, -0.5, 0.5, 6),
+    'ragged': (0.1, 0.7, 7, -3, 5, 2, 2, 2.5, 3),
+}
+
+
+def make_gentetra(path):
+    """sha-256 of the files the COMPILED reference generator (oracle/_ref/genTetranovtk) writes, per grid."""
+    import hashlib
+    import json
+    from oracle import ref_gentetra as G
+    assert G.build(), "the reference generator did not build"
+    out = {}
+    for name, grid in GENTETRA_GRIDS.items():
+        r = G.run(*grid)
+        out[name] = dict(grid=list(grid), nNode=int(r['coords'].shape[1]), nElem=int(r['conn'].shape[1]),
+                         sha_nodes=r['sha_nodes'], sha_elems=r['sha_elems'], nDBC=int(r['dbc_node'].size),
+                         sha_dbc_nodes=hashlib.sha256(r['dbc_node'].astype('<i4').tobytes()).hexdigest())
+    with open(path, 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return out
+
+
 if __name__ == '__main__':
     if not R.available():
         sys.exit("the reference tree is not here (PFEM_REFERENCE_SRC / /root/reference/src)")
+    make_gentetra(os.path.join(HERE, 'ref_gentetra.json'))
+    print('ref_gentetra.json written')
     make_elements(os.path.join(HERE, 'ref_elements.npz'))
     print('ref_elements.npz written')
     for tag in make_drivers(HERE):

@@ -104,3 +104,17 @@ def test_cuda_numbering_equals_the_executed_p_rank_driver(gpu, input_dir, name, 
     assert np.array_equal(num.part_info[own][:, [2, 3]], info[own][:, [2, 3]])
     lst, assy, edof = D.gpu_local_elements_and_assy(num, 0)
     assert np.array_equal(assy, g["assyForSoln"])
+
+
+def test_cuda_gen_tetra_writes_the_reference_generators_files(gpu):
+    """pfem_gpu_gen_tetra against the digests of the files the COMPILED reference generator writes
+    (oracle/_ref/genTetranovtk; tests/test_reference_gentetra.py), and against a live run of that binary where it is present."""
+    import test_reference_gentetra as T
+    from oracle import ref_gentetra as G
+    for name in sorted(T.GRIDS):
+        T.check_against_golden(name, M.gen_tetra_gpu(*T.GRIDS[name]["grid"]))
+    if G.available():
+        grid = (-1, 1, 24, -1, 1, 24, -1, 1, 24)
+        r, dev = G.run(*grid), M.gen_tetra_gpu(*grid)
+        assert np.array_equal(dev.coords, r["coords"]) and np.array_equal(dev.conn, r["conn"])
+        assert np.array_equal(dev.dbc_node, r["dbc_node"])
