@@ -84,12 +84,17 @@ class Result:
     pass
 
 
-def run_driver(driver_file, argv, nranks=1, partition=None, cwd='.', intent=True, quiet=True, timeout=600):
+def run_driver(driver_file, argv, nranks=1, partition=None, cwd='.', intent=True, quiet=True, timeout=600, extra_patches=None):
     """argv: the program's command-line arguments (file names).  partition: (elem_proc_id, node_proc_id), 0-based part
-    numbers, returned by the METIS mock when nranks > 1."""
+    numbers, returned by the METIS mock when nranks > 1.  extra_patches: [(old, new, count)] applied to the driver text
+    (used only to shorten a hard-coded run length, e.g. `stepsMax = 50000`)."""
     files = ELEMENT_FILES + ['solverpetsc.F', driver_file]
     tag = os.path.splitext(driver_file)[0]
-    code = F.translate(read_sources(files, intent), {'vecgetarray': mocks.vecgetarray_rewrite})
+    sources = read_sources(files, intent)
+    for old, new, n in (extra_patches or []):
+        assert sources[driver_file].count(old) == n, (old, sources[driver_file].count(old))
+        sources[driver_file] = sources[driver_file].replace(old, new)
+    code = F.translate(sources, {'vecgetarray': mocks.vecgetarray_rewrite})
     os.makedirs(OUT_DIR, exist_ok=True)
     path = os.path.join(OUT_DIR, tag + '.py')
     with open(path, 'w') as f:

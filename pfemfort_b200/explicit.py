@@ -13,6 +13,12 @@ _f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)   # noqa: E731
 _i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)     # noqa: E731
 
 
+# the explicit PROGRAM's own constants (triaelasticityexplicit.F:870-875, 957-958): single-precision literals widened
+DRIVER_ELEMDATA_TRIA = [200.0, float(np.float32(0.3)), 10.0, 1.0, 0.0, 0.0]   # E, nu, density, body force x / y
+DRIVER_TIMEDATA = [0.0, 1.0, 0.0]
+DRIVER_DT = float(np.float32(0.0002))
+
+
 def _d(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 

@@ -229,6 +229,33 @@ def make_drivers(outdir, only=None):
     return made
 
 
+# ---- explicit dynamics: the reference's central-difference PROGRAM --------------------------------------------------
+
+EXPLICIT_STEPS = 40
+
+
+def make_explicit(path, steps=EXPLICIT_STEPS):
+    """triaelasticityexplicit.F end to end on the cook membrane, one rank.  The only change to the text is the hard-coded
+    run length (`stepsMax = 50000` -> `steps`); material data, dt = 0.0002 (single-precision literal) and the load switch
+    are the program's own.  Recorded: the lumped mass, the state after `steps` steps, every solnoutput.dat record."""
+    with tempfile.TemporaryDirectory() as wd:
+        stage_inputs(wd)
+        name = 'cookmembranetria32'
+        argv = [f'{name}-nodes.dat', f'{name}-elems.dat', f'{name}-DirichBC.dat', f'{name}-ForceBC.dat']
+        res = R.run_driver('triaelasticityexplicit.F', argv, 1, cwd=wd,
+                           extra_patches=[('stepsMax = 50000', f'stepsMax = {steps}', 1)])
+    assert res.stopped is None, res.stopped
+    fa, fl = res.ranks[0].final_arrays, res.ranks[0].final_locals
+    out = dict(globalM=fa['globalm'], disp=fa['disp'], dispPrev=fa['dispprev'], dispPrev2=fa['dispprev2'], velo=fa['velo'],
+               acce=fa['acce'], elemData=fa['elemdata'][:6], timeData=fa['timedata'][:3], dt=np.float64(fl['dt']),
+               steps=np.int32(fl['stepscompleted']), timeNow=np.float64(fl['timenow']),
+               solnoutput=np.array(res.ranks[0].written['solnoutput.dat'], np.float64),
+               assyForSoln=fa['assyforsoln'].astype(np.int32))
+    if path:
+        np.savez_compressed(path, **out)
+    return out
+
+
 # ---- the compiled mesh generator ----------------------------------------------------------------------------------------
 
 GENTETRA_GRIDS = {
@@ -268,3 +295,5 @@ if __name__ == '__main__':
     print('ref_elements.npz written')
     for tag in make_drivers(HERE):
         print('ref_driver_%s.npz written' % tag)
+    make_explicit(os.path.join(HERE, 'ref_explicit_cookmembranetria32.npz'))
+    print('ref_explicit_cookmembranetria32.npz written')

@@ -184,6 +184,34 @@ def test_shipped_beam_file_stops_with_negative_jacobian():
     assert list(_driver("beam3Dtet6366", 1)["shipped_stop_line"]) == [321]
 
 
+# ---- explicit dynamics: the reference's central-difference PROGRAM, executed --------------------------------
+
+def test_oracle_explicit_time_loop_equals_the_executed_program(input_dir):
+    """triaelasticityexplicit.F run end to end (40 steps, cook membrane): lumped mass, state and every solnoutput.dat record
+    bit for bit; the program's own material data and time step are what explicit.DRIVER_* hold."""
+    from pfemfort_b200 import explicit as X
+    g = np.load(os.path.join(GOLDEN, "ref_explicit_cookmembranetria32.npz"))
+    assert np.array_equal(g["elemData"], X.DRIVER_ELEMDATA_TRIA) and float(g["dt"]) == X.DRIVER_DT
+    assert np.array_equal(g["timeData"][1:], X.DRIVER_TIMEDATA[1:])        # timeData(1) is never set by the program
+    m, kind = _mesh("cookmembranetria32", input_dir)
+    num = D.number(m, kind)
+    fs = X.free_slots(num)
+    assert np.array_equal(fs, g["assyForSoln"])
+    Mg, nbad = O.explicit_lumped_mass(kind, num.conn_new, m.coords, X.DRIVER_ELEMDATA_TRIA)
+    assert nbad == 0 and np.array_equal(Mg, g["globalM"])
+    st, t = None, 0.0
+    for k in range(int(g["steps"])):
+        st = O.explicit_advance(kind, num.conn_new, m.coords, fs, X.DRIVER_ELEMDATA_TRIA, X.DRIVER_TIMEDATA, X.DRIVER_DT, 1, Mg,
+                                state=st)
+        rec = g["solnoutput"][k]                  # timeNow, disp(671), disp(672), velo(671), velo(672)   (:1055)
+        assert rec[0] == t and [st["disp"][670], st["disp"][671], st["velo"][670], st["velo"][671]] == list(rec[1:])
+        t = t + X.DRIVER_DT
+    assert t == float(g["timeNow"])
+    for key in ("disp", "dispPrev2", "velo", "acce"):
+        assert np.array_equal(st[key], g[key]), key
+    assert np.abs(g["disp"]).max() > 0
+
+
 # ---- the generator still reproduces the committed files (build container only) --------------------------------------
 
 def _reference_present():
@@ -202,6 +230,9 @@ def test_regenerated_vectors_equal_the_committed_files(tmp_path):
     assert set(new) == set(old.files)
     for k in old.files:
         assert np.array_equal(new[k], old[k]), k
+    new = gen.make_explicit(None, steps=3)
+    old = np.load(os.path.join(GOLDEN, "ref_explicit_cookmembranetria32.npz"))
+    assert np.array_equal(new["globalM"], old["globalM"]) and np.array_equal(new["solnoutput"], old["solnoutput"][:3])
     for tag, data in gen.make_drivers(None, only={"tria20x20_p3", "tet10_p2"}).items():
         old = np.load(os.path.join(GOLDEN, f"ref_driver_{tag}.npz"))
         for k in old.files:
