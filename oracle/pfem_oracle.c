@@ -7,16 +7,30 @@
  * legs may load this file's shared object.  The product library (libpfemb200.so)
  * never links, loads or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or timings
- * (SURVEY.md section 4), and it cannot be compiled here (no Fortran compiler, MPI or
- * PETSc).  What pins this oracle instead: the analytic known answers baked into
- * the reference's own BC fixtures (tria20x20: Laplace solution; tet10:
- * u = x^2+y^2+z^2 with source -6), the independent closed-form Ke of
- * triapoissonserialimpl1.F:580-594, and the identities (row sums, volumes) checked
- * in tests/test_oracle.py.  PETSc (3.6.4, pinned only by the path string at
- * CMakeLists.txt:43) is a third-party dependency absent from /root/reference;
- * its MatSetValues / KSPSolve_CG / PCApply_Jacobi semantics are restated here
- * from its published behaviour and anchored on the reference's call sites.
+ * PARITY: PINNED BY RUNNING THE REFERENCE'S OWN SOURCE (round 2).  The reference ships no
+ * tests, golden vectors or timings and its Fortran + PETSc + MPI
+ * programs cannot be compiled here (no gfortran / MPI / PETSc).  Instead they are EXECUTED
+ * from /root/reference/src by oracle/refrun (a Fortran-subset -> Python translator with
+ * Fortran's typing and rounding rules; PETSc / MPI / METIS / the VTK writer, which are
+ * external to the reference, come from oracle/refrun/mocks.py), and what those runs
+ * produce is committed as tests/golden/ref_*.npz by tests/golden/make_reference_vectors.py:
+ *   - the eight element routines of the path on seeded random elements, incl. where
+ *     the reference STOPs                                      -> orc_*_ke, orc_residual_*, orc_mass_*
+ *   - the four *parallelimpl1 PROGRAMs end to end on the bundled inputs, 1..4 simulated
+ *     ranks: numbering, ElemDofArray, the Mat / Vec handed to KSPSolve, solver options
+ *                                                              -> orc_number_dofs, orc_pattern, orc_assemble, ...
+ *   - triaelasticityexplicit.F end to end (40 steps)           -> orc_explicit_*
+ * tests/test_reference_vectors.py holds every function here to those files BIT FOR BIT
+ * (P > 1 ranks: integers bit for bit, values to 1e-12 -- the reference's own sums then
+ * depend on PETSc's stash order).  The mesh generator, the one program of the reference
+ * that compiles with g++ alone, is built as oracle/_ref/genTetranovtk (make ref).
+ * NOT pinned by a reference run: the Krylov iterates (KSPSolve is PETSc's, a third-party
+ * dependency absent from /root/reference, pinned only by the path string at
+ * CMakeLists.txt:43).  Its MatSetValues / KSPSolve_CG / PCApply_Jacobi / PCBJACOBI+ILU(0)
+ * semantics are restated from its published behaviour and anchored on the reference's
+ * call sites, on the analytic answers baked into the reference's BC fixtures (tria20x20:
+ * Laplace solution; tet10: u = x^2+y^2+z^2 with source -6), on the closed-form Ke of
+ * triapoissonserialimpl1.F:580-594 and on the identities in tests/test_oracle.py.
  *
  * Arithmetic conventions reproduced:
  *   - gfortran without -fdefault-real-8: every real literal is SINGLE precision,

@@ -1,7 +1,8 @@
 """ctypes front-end of the C oracle (oracle/pfem_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
-PARITY UNPINNED: the reference has no golden vectors; see the header of pfem_oracle.c for what pins it.
+PARITY: pinned by golden vectors produced by executing the reference's own source (oracle/refrun ->
+tests/golden/ref_*.npz, tests/test_reference_vectors.py); the Krylov iterates (PETSc's) are not.  See pfem_oracle.c.
 """
 from __future__ import annotations
 

@@ -1,6 +1,6 @@
 """CPU tests of the oracle (the checker): known answers of the reference's own fixtures, the independent
-closed-form Ke, and the identities of SURVEY.md section 8(c).  PARITY UNPINNED by golden vectors (the reference
-ships none); these are the pins that exist."""
+closed-form Ke, and the identities of SURVEY.md section 8(c).  (The golden vectors produced by executing the reference's own
+source are in tests/test_reference_vectors.py; the pins here are independent of them.)"""
 import os
 
 import numpy as np
