@@ -140,6 +140,40 @@ def test_oracle_system_equals_what_the_executed_driver_hands_to_petsc(input_dir,
         assert P.vector_within(rhs, g["rhs"], 1e-12)
 
 
+@pytest.mark.parametrize("name,p", [c for c in CASE_IDS if c[1] > 1])
+def test_rank_block_decomposition_equals_the_executed_p_rank_driver(input_dir, name, p):
+    """The decomposition the multi-GPU path uses (every rank assembles ITS rows from the owned + overlap elements,
+    driver.local_elements; no assembly collective) against what the reference's P ranks produce together through PETSc's
+    stash: same pattern block, values to 1e-12, and every row block bit-identical to the ONE-rank sum order."""
+    g = _driver(name, p)
+    m, kind = _mesh(name, input_dir)
+    ndof = S.KIND_DIMS[kind][1]
+    num = D.number(m, kind, p, g["node_proc_id"])
+    grp, gcol = O.pattern(num.elemDof, num.size_global)
+    assert np.array_equal(grp, g["rowptr"]) and np.array_equal(gcol, g["col"])
+    vals, rhss, handed = [], [], np.zeros(m.nElem, bool)
+    for r in range(p):
+        lo, hi = num.row_range(r)
+        lst = D.local_elements(num, r)
+        handed[lst] = True
+        # the reference hands element e to rank elem_proc_id(e) only; here every rank with a row of e computes it
+        mine = np.flatnonzero(g["elem_proc_id"] == r)
+        touching = mine[(num.elemDof[:, mine] >= 0).any(axis=0)]
+        own_rows = ((num.elemDof[:, touching] >= lo) & (num.elemDof[:, touching] < hi)).any(axis=0)
+        assert np.isin(touching[own_rows], lst).all()
+        val, rhs, nbad = O.assemble(kind, np.ascontiguousarray(num.conn_new[:, lst]), m.coords, num.node_map_get_old,
+                                    np.ascontiguousarray(num.elemDof[:, lst]), num.solnApplied, D.DEFAULT_ELEMDATA[kind],
+                                    D.DEFAULT_TIMEDATA, grp, gcol, row_lo=lo, row_hi=hi)
+        assert nbad == 0
+        vals.append(val[grp[lo]:grp[hi]])
+        rhss.append(rhs[lo:hi])
+    val, rhs = np.concatenate(vals), np.concatenate(rhss)
+    if m.fbc_node.size:
+        O.add_force_bc(rhs, m.fbc_node, m.fbc_dof, m.fbc_val, ndof, num.node_map_get_new, num.NodeDofArrayNew, num.size_global)
+    assert P.values_within(grp, val, g["val"], 1e-12) and P.vector_within(rhs, g["rhs"], 1e-12)
+    assert np.array_equal(handed, (num.elemDof >= 0).any(axis=0))
+
+
 @pytest.mark.parametrize("name,p", CASE_IDS)
 def test_solver_options_and_call_order_of_the_executed_wrapper(name, p):
     """solverpetsc.F as executed: KSPCG + PCBJACOBI (:187, :206), the three Mat options, negative indices ignored in the
