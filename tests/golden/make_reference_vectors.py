@@ -134,7 +134,7 @@ CASES = {
     'tria20x20': ('triapoissonparallelimpl1.F', 'tria20x20', 0, False, False, (1, 3)),
     'tet10': ('tetrapoissonparallelimpl1.F', 'tet10', 1, False, False, (1, 2, 4)),
     'cookmembranetria32': ('triaelasticityparallelimpl1.F', 'cookmembranetria32', 2, True, False, (1, 2)),
-    'beam3Dtet6366': ('tetraelasticityparallelimpl1.F', 'beam3Dtet6366', 3, True, True, (1,)),
+    'beam3Dtet6366': ('tetraelasticityparallelimpl1.F', 'beam3Dtet6366', 3, True, True, (1, 2)),
 }
 
 

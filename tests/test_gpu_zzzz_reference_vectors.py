@@ -84,7 +84,8 @@ def test_cuda_system_equals_what_the_executed_driver_hands_to_petsc(gpu, input_d
     s.free()
 
 
-@pytest.mark.parametrize("name,p", [("tria20x20", 3), ("tet10", 2), ("tet10", 4), ("cookmembranetria32", 2)])
+@pytest.mark.parametrize("name,p", [("tria20x20", 3), ("tet10", 2), ("tet10", 4), ("cookmembranetria32", 2),
+                                    ("beam3Dtet6366", 2)])
 def test_cuda_numbering_equals_the_executed_p_rank_driver(gpu, input_dir, name, p):
     """P simulated ranks of the reference: the GPU numbering block (csrc/gpu_setup.cu) with the reference run's node
     partition, bit for bit -- renumbering, NodeDofArrayNew, ElemDofArray, applied values, per-rank node / row ranges,

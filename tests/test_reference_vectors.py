@@ -16,13 +16,16 @@ from oracle import pyoracle as O
 from pfemfort_b200 import driver as D, mesh as M, solver as S
 import properties as P
 
+# the executed reference divides by a zero Jacobian on degenerate elements exactly like the compiled one would (inf / NaN)
+pytestmark = pytest.mark.filterwarnings("ignore::RuntimeWarning")
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = [S.POISSON_TRIA, S.POISSON_TETRA, S.ELASTICITY_TRIA, S.ELASTICITY_TETRA]
 CASES = {  # name: (kind, swap_34, rank counts)
     "tria20x20": (S.POISSON_TRIA, False, (1, 3)),
     "tet10": (S.POISSON_TETRA, False, (1, 2, 4)),
     "cookmembranetria32": (S.ELASTICITY_TRIA, False, (1, 2)),
-    "beam3Dtet6366": (S.ELASTICITY_TETRA, True, (1,)),
+    "beam3Dtet6366": (S.ELASTICITY_TETRA, True, (1, 2)),
 }
 CASE_IDS = [(n, p) for n, spec in CASES.items() for p in spec[2]]
 
@@ -251,6 +254,45 @@ def test_oracle_explicit_time_loop_equals_the_executed_program(input_dir):
 def _reference_present():
     from oracle.refrun import run_reference as R
     return R.available()
+
+
+@pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_against_a_live_run_of_the_reference_routines(kind):
+    """1000 fresh random elements per kind (other seeds, sizes from 1e-6 to 1e+4, offsets up to 1e+5, near-degenerate shapes)
+    through the reference's element routines executed live, against the oracle: bit for bit, same STOPs."""
+    from oracle.refrun import run_reference as R
+    from oracle.refrun.runtime import FortranStop
+    ns = R.element_routines(intent=True)
+    names = {S.POISSON_TRIA: "stiffnessresidualpoissonlineartria", S.POISSON_TETRA: "stiffnessresidualpoissonlineartetra",
+             S.ELASTICITY_TRIA: "stiffnessresidualelasticitylineartria", S.ELASTICITY_TETRA: "stiffnessresidualelasticitylineartetra"}
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    nsz = npe * ndof
+    rng = np.random.default_rng(20261017 + kind)
+    stops = 0
+    for e in range(1000):
+        scale = 10.0 ** rng.uniform(-6, 4)
+        p = rng.standard_normal((npe, ndim)) * scale + rng.standard_normal(ndim) * 10.0 ** rng.uniform(-3, 5)
+        if e % 7 == 0:                                   # a sliver: last node almost in the span of the others
+            p[-1] = p[:-1].mean(axis=0) + 1e-7 * scale * rng.standard_normal(ndim)
+        xyz = [np.array(p[:, d]) for d in range(ndim)]
+        ed = np.zeros(50)
+        ed[:6] = [rng.uniform(0.1, 500.0), rng.uniform(0.0, 0.49), rng.uniform(0.1, 3.0), *rng.standard_normal(3)]
+        td = np.zeros(50)
+        td[1:3] = rng.uniform(0.1, 1.0, 2)
+        vc = rng.standard_normal(nsz)
+        K, F = np.full((nsz, nsz), np.nan, order="F"), np.full(nsz, np.nan)
+        try:
+            ns[names[kind]](*xyz, ed.copy(), td.copy(), vc.copy(), np.zeros(nsz), K, F)
+            stop = False
+        except FortranStop:
+            stop = True
+        Ko, Fo, rc = O.element_ke(kind, xyz[0], xyz[1], xyz[2] if ndim == 3 else None, ed[:8], td[:4], vc)
+        assert stop == (rc != 0)
+        stops += stop
+        if not stop:
+            assert np.array_equal(K, Ko, equal_nan=True) and np.array_equal(F, Fo, equal_nan=True), (kind, e)
+    assert 100 < stops < 900
 
 
 @pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
