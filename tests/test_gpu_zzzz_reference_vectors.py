@@ -142,3 +142,29 @@ def test_cuda_explicit_time_loop_equals_the_executed_program(gpu, input_dir):
     for key in ("disp", "dispPrev2", "velo", "acce"):
         assert np.array_equal(st[key], g[key]), key
     ex.free()
+
+
+def test_the_references_own_program_with_the_integration_diff_runs_on_the_library(gpu, tmp_path):
+    """tetrapoissonparallelimpl1.F, read from the reference tree, with the INTEGRATION.md diff applied to its text, executed
+    statement by statement (oracle/refrun/dropin.py) against the real ctypes binding of libpfemb200.so: everything the diff
+    does not touch is the reference's own code.  The translated program is an oracle/_ref/ artefact made by build() where the
+    reference tree is (it travels with the snapshot, like oracle/_ref/genTetranovtk)."""
+    import gzip
+    from oracle.refrun import dropin
+    if not dropin.available():
+        pytest.skip("oracle/_ref/dropin_tetrapoissonparallelimpl1.py was not built (no reference tree at build time)")
+    argv = []
+    for kind in ("nodes", "elems", "DirichBC"):
+        with gzip.open(os.path.join(GOLDEN, "input", f"tet10-{kind}.dat.gz")) as g_, open(tmp_path / f"tet10-{kind}.dat", "wb") as o:
+            o.write(g_.read())
+        argv.append(f"tet10-{kind}.dat")
+    bridge, rt = dropin.run("tetrapoissonparallelimpl1.F", argv, S.SolverB200, cwd=str(tmp_path))
+    g = np.load(os.path.join(GOLDEN, "ref_driver_tet10_p1.npz"))
+    c = bridge.captured
+    assert np.array_equal(c["rowptr"], g["rowptr"]) and np.array_equal(c["col"], g["col"])
+    assert np.array_equal(c["val"], g["val"]) and np.array_equal(c["rhs"], g["rhs"])
+    assert c["info"]["reason"] > 0 and c["info"]["its"] > 0
+    rec = rt.written["temp.dat"]
+    assert np.array_equal(np.array([[r[0], r[1]] for r in rec]), g["temp_dat_index"])
+    x = np.array([r[2] for r in rec])
+    assert np.abs(x - g["temp_dat_value"]).max() <= 1e-4 * np.abs(g["temp_dat_value"]).max()
