@@ -177,3 +177,57 @@ def run(driver_file, argv, backend, cwd='.'):
     ns[prog[0]]()
     assert len(Bridge.created) == 1
     return Bridge.created[0], rt
+
+
+# ---- the same, through the real Fortran module ------------------------------------------------------------------------
+
+MODULE_FILE = R.os.path.join(R.os.path.dirname(R.os.path.dirname(R.os.path.dirname(R.os.path.abspath(__file__)))), 'include',
+                             'pfem_b200.f90')
+
+
+def module_program_path(driver_file):
+    return R.os.path.join(R.OUT_DIR, 'dropin_f90_' + R.os.path.splitext(driver_file)[0] + '.py')
+
+
+def build_module_program(driver_file='tetrapoissonparallelimpl1.F'):
+    """the edited PROGRAM + include/pfem_b200.f90 itself (not the python Bridge), translated into oracle/_ref/."""
+    sources = R.read_sources(R.ELEMENT_FILES, intent=True)
+    with open(MODULE_FILE) as f:
+        sources['pfem_b200.f90'] = f.read()
+    sources[driver_file] = patched_source(driver_file)
+    code = F.translate(sources, {'vecgetarray': mocks.vecgetarray_rewrite}, static_zero_programs=True)
+    R.os.makedirs(R.OUT_DIR, exist_ok=True)
+    with open(module_program_path(driver_file), 'w') as f:
+        f.write(code)
+    return module_program_path(driver_file)
+
+
+def module_available(driver_file='tetrapoissonparallelimpl1.F'):
+    return R.available() or R.os.path.exists(module_program_path(driver_file))
+
+
+def run_through_module(driver_file, argv, clib, cwd='.', before_free=None):
+    """execute the edited PROGRAM with `Module_SolverB200` = the translated include/pfem_b200.f90, its BIND(C) interfaces bound
+    to `clib` (a ctypes.CDLL: the real libpfemb200.so, or the test double of tests/fake_abi).  `before_free(handle)` is
+    called just before the PROGRAM's own `call solverpetsc%free()` releases the handle.  Returns the Runtime."""
+    from .runtime import set_clib
+    path = build_module_program(driver_file) if R.available() else module_program_path(driver_file)
+    with open(path) as f:
+        code = f.read()
+    world = mocks.World(1)
+    rt = Runtime([driver_file] + list(argv), cwd, 0, world, True)
+    _rt.bind(rt)
+    set_clib(clib)
+    ns = dict(mocks.namespace())
+    exec(compile(code, path, 'exec'), ns)
+    if before_free is not None:
+        real_free = ns['pfem_solver_free']
+
+        def free_hook(h):
+            before_free(h.v if hasattr(h, 'v') else h)
+            return real_free(h)
+        ns['pfem_solver_free'] = free_hook
+    prog = [k for k in ns if k.startswith('program_')]
+    assert len(prog) == 1
+    ns[prog[0]]()
+    return rt

@@ -93,6 +93,31 @@ def logical_statements(text: str):
     return out
 
 
+def logical_statements_free(text: str):
+    """Free-form source (.f90): `&` continuations, `!` comments anywhere, `;` separators."""
+    joined, cont = [], False
+    for no, raw in enumerate(text.splitlines(), 1):
+        if raw.startswith('#'):
+            continue
+        st = _strip_comment(raw).strip()
+        if not st:
+            continue
+        if cont:
+            if st.startswith('&'):
+                st = st[1:].lstrip()
+            nxt = st.endswith('&')
+            joined[-1][1] += ' ' + (st[:-1].rstrip() if nxt else st)
+            cont = nxt
+            continue
+        cont = st.endswith('&')
+        joined.append([no, st[:-1].rstrip() if cont else st])
+    out = []
+    for no, s in joined:
+        for part in _split_semicolons(s):
+            out.append((no, part))
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # tokens and expressions
 # --------------------------------------------------------------------------------------------------------------------
@@ -382,6 +407,17 @@ class Sym:
     init: str | None = None
     alloc: bool = False
     pointer: bool = False
+    value: bool = False
+    optional: bool = False
+
+
+@dataclass
+class Interface:
+    """one BIND(C) function of an INTERFACE block: what a call has to marshal."""
+    name: str
+    args: list
+    syms: dict
+    result: str
 
 
 @dataclass
@@ -400,6 +436,7 @@ class TypeDef:
     name: str
     fields: dict = field(default_factory=dict)   # name -> typ
     procs: list = field(default_factory=list)
+    inits: dict = field(default_factory=dict)    # name -> initialiser source or None
 
 
 _DECL_RE = re.compile(
@@ -427,11 +464,19 @@ def parse_decl(stmt: str, syms: dict, dummies: set):
         typ, rest = 'd', s[m.end():]
     elif low.startswith('integer'):
         typ, rest = 'i', s[7:]
+        if rest.lstrip().startswith('('):               # kind selector: INTEGER(C_INT), INTEGER(C_LONG_LONG)
+            r2 = rest.lstrip()
+            rest = r2[_match_paren(r2, 0) + 1:]
     elif low.startswith('real'):
         typ, rest = 'r', s[4:]
         mm = re.match(r'^\s*(\(\s*(kind\s*=\s*)?8\s*\)|\*\s*8)', rest, re.I)
         if mm:
             typ, rest = 'd', rest[mm.end():]
+        elif rest.lstrip().startswith('('):            # REAL(C_DOUBLE) / REAL(C_FLOAT)
+            r2 = rest.lstrip()
+            e = _match_paren(r2, 0)
+            typ = 'd' if 'double' in r2[:e].lower() else 'r'
+            rest = r2[e + 1:]
     elif low.startswith('logical'):
         typ, rest = 'l', s[7:]
     elif low.startswith('character'):
@@ -447,6 +492,8 @@ def parse_decl(stmt: str, syms: dict, dummies: set):
         st = s.index('(')
         e = _match_paren(s, st)
         typ, rest = 't:' + s[st + 1:e].strip().lower(), s[e + 1:]
+        if typ == 't:c_ptr':
+            typ = 'h'                                   # TYPE(C_PTR): an opaque handle
     else:
         first = re.match(r'^([A-Za-z_]\w*)\s+', s)
         typ = MACRO_TYPES[first.group(1).lower()]
@@ -457,7 +504,7 @@ def parse_decl(stmt: str, syms: dict, dummies: set):
     if not _:
         # old style "INTEGER a, b" without ::
         attrs_s, ents = '', rest
-    dims_attr, param, alloc, pointer = None, False, False, False
+    dims_attr, param, alloc, pointer, value, optional = None, False, False, False, False, False
     for a in split_top(attrs_s):
         al = a.strip().lower()
         if not al:
@@ -471,7 +518,11 @@ def parse_decl(stmt: str, syms: dict, dummies: set):
             alloc = True
         elif al == 'pointer':
             pointer = True
-        elif al.startswith('intent') or al in ('save', 'optional', 'target'):
+        elif al == 'value':
+            value = True
+        elif al == 'optional':
+            optional = True
+        elif al.startswith('intent') or al in ('save', 'target', 'public', 'private'):
             pass
         else:
             raise Unsupported(f"declaration attribute {a!r} in {stmt!r}")
@@ -506,17 +557,17 @@ def parse_decl(stmt: str, syms: dict, dummies: set):
         if not re.match(r'^[A-Za-z_]\w*$', name):
             raise Unsupported(f"entity {ent!r} in {stmt!r}")
         name = name.lower()
-        syms[name] = Sym(name, typ, dims, name in dummies, param, init, alloc, pointer)
+        syms[name] = Sym(name, typ, dims, name in dummies, param, init, alloc, pointer, value, optional)
 
 
 # --------------------------------------------------------------------------------------------------------------------
 # units
 # --------------------------------------------------------------------------------------------------------------------
 
-def parse_file(text: str):
-    """-> (units, typedefs, module_params) of one source file."""
-    stmts = logical_statements(text)
-    units, typedefs, mod_syms = [], {}, {}
+def parse_file(text: str, free_form: bool = False):
+    """-> (units, typedefs, module_params, interfaces) of one source file."""
+    stmts = logical_statements_free(text) if free_form else logical_statements(text)
+    units, typedefs, mod_syms, interfaces = [], {}, {}, {}
     i, module = 0, None
     cur = None          # current Unit
     in_type = None
@@ -533,9 +584,36 @@ def parse_file(text: str):
             if re.match(r'^end\s*module', low):
                 module = None
                 continue
-            if low.startswith('use ') or low.startswith('implicit') or low == 'contains':
+            if re.match(r'^use\b', low) or low.startswith('implicit') or low in ('contains', 'private', 'public'):
                 continue
-            m = re.match(r'^type\s+(\w+)$', low)
+            if low == 'interface':
+                # BIND(C) function interfaces: what each call has to marshal
+                fn = None
+                while True:
+                    no, s = stmts[i]
+                    i += 1
+                    low = s.lower().strip()
+                    if re.match(r'^end\s*interface', low):
+                        break
+                    if fn is None:
+                        m = re.match(r'^(.*?)\bfunction\s+(\w+)\s*\((.*?)\)\s*(bind\s*\(.*\))?\s*$', s.strip(), re.I | re.S)
+                        if not m:
+                            raise Unsupported(f"line {no}: only FUNCTION interfaces are supported: {s!r}")
+                        rt = m.group(1).strip().lower()
+                        res = 'i' if rt.startswith('integer') else ('d' if 'double' in rt else ('r' if rt.startswith('real') else None))
+                        fn = Interface(m.group(2).lower(), [a.strip().lower() for a in split_top(m.group(3)) if a.strip()], {}, res)
+                    elif re.match(r'^end\s*function', low):
+                        for a in fn.args:
+                            if a not in fn.syms:
+                                raise Unsupported(f"line {no}: interface {fn.name}: dummy {a} is not declared")
+                        interfaces[fn.name] = fn
+                        fn = None
+                    elif low.startswith('import') or re.match(r'^use\b', low) or low.startswith('implicit'):
+                        pass
+                    else:
+                        parse_decl(s, fn.syms, set(fn.args))
+                continue
+            m = re.match(r'^type\s*(?:,\s*\w+\s*)*(?:::)?\s*(\w+)$', low)
             if m and module:
                 in_type = TypeDef(m.group(1))
                 continue
@@ -570,6 +648,7 @@ def parse_file(text: str):
                 parse_decl(s, tmp, set())
                 for k, v in tmp.items():
                     in_type.fields[k] = v.typ
+                    in_type.inits[k] = v.init
             continue
         # inside a unit
         if re.match(r'^end\s*(program|subroutine)?(\s+\w+)?$', low) and not re.match(r'^end\s*(if|do|select|type)', low):
@@ -577,7 +656,7 @@ def parse_file(text: str):
             cur = None
             continue
         if in_decl:
-            if low.startswith('use ') or low.startswith('implicit'):
+            if re.match(r'^use\b', low) or low.startswith('implicit'):
                 continue
             if _is_decl(s):
                 parse_decl(s, cur.syms, set(cur.args))
@@ -586,7 +665,7 @@ def parse_file(text: str):
         cur.body.append((no, s))
     if cur is not None:
         raise Unsupported("unterminated program unit " + cur.name)
-    return units, typedefs, mod_syms
+    return units, typedefs, mod_syms, interfaces
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -596,15 +675,19 @@ def parse_file(text: str):
 INTRINSIC_FUNCS = {'min', 'max', 'abs', 'sqrt', 'acos', 'asin', 'atan', 'cos', 'sin', 'tan', 'exp', 'log', 'dble',
                    'real', 'int', 'nint', 'mod', 'size', 'matmul', 'transpose', 'trim', 'adjustl', 'len_trim',
                    'iargc', 'command_argument_count', 'allocated', 'null', 'float', 'sum', 'dot_product', 'sign',
-                   'floor', 'ceiling', 'huge', 'tiny', 'epsilon', 'maxval', 'minval'}
+                   'floor', 'ceiling', 'huge', 'tiny', 'epsilon', 'maxval', 'minval', 'present'}
 
 _PROMO = {'i': 0, 'r': 1, 'd': 2}
 
 
 class Gen:
-    def __init__(self, unit: Unit, typedefs: dict, mod_syms: dict, all_units: dict, rewrites=None, consts=None):
+    def __init__(self, unit: Unit, typedefs: dict, mod_syms: dict, all_units: dict, rewrites=None, consts=None,
+                 interfaces=None):
         self.u = unit
         self.consts = consts if consts is not None else {}
+        self.interfaces = interfaces or {}
+        self.pre, self.post = [], []      # statements hoisted around the current one (by-reference C arguments)
+        self.zero_fill = False
         self.typedefs = typedefs
         self.mod_syms = mod_syms
         self.all_units = all_units
@@ -616,7 +699,34 @@ class Gen:
 
     # ---- helpers
     def emit(self, s):
+        if self.pre:
+            pre, self.pre = self.pre, []
+            for p in pre:
+                self.lines.append('    ' * self.ind + p)
         self.lines.append('    ' * self.ind + s)
+
+    def c_call(self, n, args):
+        """call of a BIND(C) interface function inside an expression: VALUE dummies by value, arrays as arrays, other
+        scalars by reference (component -> attribute reference; local -> a Ref hoisted before the statement and written
+        back after it)."""
+        itf = self.interfaces[n]
+        if len(args) != len(itf.args):
+            raise Unsupported(f"{n}: {len(args)} actual arguments for {len(itf.args)} dummies")
+        out = []
+        for a, dn in zip(args, itf.args):
+            d = itf.syms[dn]
+            if d.value or d.dims is not None:
+                out.append(self.ex(a))
+            elif a[0] == 'comp' and a[3] is None:
+                out.append(f'_AttrRef({self.ex(a[1])}, {mangle(a[2])!r})')
+            elif a[0] == 'name' and self.sym(a[1]) is not None and self.sym(a[1]).dims is None and not self.sym(a[1]).param:
+                t = self.newtmp('_c')
+                self.pre.append(f'{t} = Ref({mangle(a[1])})')
+                self.post.append((a, t))
+                out.append(t)
+            else:
+                out.append(f'Ref({self.ex(a)})')
+        return f'{mangle(n)}({", ".join(out)})'
 
     def sym(self, n):
         return self.u.syms.get(n) or self.mod_syms.get(n)
@@ -647,6 +757,8 @@ class Gen:
             if s and s.dims is not None:
                 return s.typ if s.typ in 'irdlc' else None
             n = e[1]
+            if n in self.interfaces:
+                return self.interfaces[n].result
             if n in ('min', 'max', 'mod', 'abs', 'sign', 'sum', 'maxval', 'minval'):
                 ts = [self.typeof(a) for a in e[2]]
                 if any(t not in _PROMO for t in ts):
@@ -751,6 +863,8 @@ class Gen:
                 lo = '' if a[1] is None else f'{self.int_expr(a[1])}-1'
                 hi = '' if a[2] is None else self.int_expr(a[2])
                 return f'{mangle(n)}[{lo}:{hi}]'
+            if n in self.interfaces:
+                return self.c_call(n, args)
             if n in INTRINSIC_FUNCS:
                 return f'_in_{n}({", ".join(self.ex(a) for a in args)})'
             # external function (MPI_Wtime ...): provided by the mocks, scalars by value
@@ -871,7 +985,14 @@ class Gen:
         stack = []   # entries: ('if',) ('do', name) ('select', tmp, first)
         for no, s in body:
             try:
+                depth = len(stack)
                 self.gen_stmt(no, s, stack)
+                if self.post:
+                    if len(stack) != depth:
+                        raise Unsupported("by-reference C argument in a block header")
+                    post, self.post = self.post, []
+                    for a, t in post:
+                        self.assign_to(a, f'{t}.v', None)
             except Unsupported as ex:
                 raise Unsupported(f"{self.u.name} line {no}: {ex}   [{s}]") from None
         if stack:
@@ -1204,7 +1325,7 @@ class Gen:
     def gen_unit(self):
         u = self.u
         fname = mangle(u.name) if u.kind == 'subroutine' else 'program_' + u.name.lower()
-        params = [mangle(a) + '__a' for a in u.args]
+        params = [mangle(a) + '__a' + ('=None' if (u.syms.get(a) and u.syms[a].optional) else '') for a in u.args]
         self.lines.append(f'def {fname}({", ".join(params)}):')
         save_key = f'_save_{fname}'
         saved = []
@@ -1216,6 +1337,8 @@ class Gen:
                 raise Unsupported(f"{u.name}: dummy {a} is not declared")
             if s.dims is not None or s.typ.startswith('t:'):
                 self.emit(f'{mangle(a)} = {mangle(a)}__a')
+            elif s.optional:
+                self.emit(f'{mangle(a)} = {mangle(a)}__a.v if {mangle(a)}__a is not None else None')
             else:
                 self.emit(f'{mangle(a)} = {mangle(a)}__a.v')
                 scalars_out.append(a)
@@ -1234,7 +1357,7 @@ class Gen:
                 dims = ', '.join(self.int_expr(parse_expr(d)) for d in s.dims)
                 if s.init is not None:
                     raise Unsupported("array initialiser")
-                self.emit(f'{mangle(n)} = _alloc({s.typ!r}, ({dims},))')
+                self.emit(f'{mangle(n)} = _alloc({s.typ!r}, ({dims},){", zero=True" if self.zero_fill else ""})')
             elif s.init is not None:
                 saved.append(n)
                 self.emit(f'{mangle(n)} = {save_key}.get({n!r}, _UNSET)')
@@ -1260,18 +1383,24 @@ class Gen:
         return '\n'.join(head + self.lines) + '\n'
 
 
-def translate(sources: dict, rewrites=None) -> str:
-    """sources: {file name: text} -> python module text (functions of every unit, classes of every TYPE)."""
-    all_units, typedefs, mod_syms = {}, {}, {}
+def translate(sources: dict, rewrites=None, static_zero_programs: bool = False) -> str:
+    """sources: {file name: text} -> python module text (functions of every unit, classes of every TYPE, one ctypes
+    binding per BIND(C) interface function).  Files named *.f90 are free-form, everything else fixed-form."""
+    all_units, typedefs, mod_syms, interfaces = {}, {}, {}, {}
     per_file = []
     for fn, text in sources.items():
-        units, tds, ms = parse_file(text)
+        units, tds, ms, itf = parse_file(text, free_form=fn.lower().endswith('.f90'))
         per_file.append((fn, units, ms))
         typedefs.update(tds)
+        interfaces.update(itf)
+        mod_syms.update({k: v for k, v in ms.items() if v.param})    # module PARAMETERs are visible to every USEr
         for u in units:
             all_units[u.name] = u
     out = []
     consts = {}
+    for name, itf in interfaces.items():
+        spec = [(itf.syms[a].typ, itf.syms[a].value, itf.syms[a].dims is not None) for a in itf.args]
+        out.append(f'{mangle(name)} = _cbind({name!r}, {spec!r}, {itf.result!r})')
     for fn, units, ms in per_file:
         out.append(f'# ---- {fn}')
         # module-level parameters
@@ -1279,16 +1408,24 @@ def translate(sources: dict, rewrites=None) -> str:
         for n, s in ms.items():
             if s.param:
                 out.append(f'{mangle(n)} = {g.conv(s.typ, parse_expr(s.init))}')
+        scope = dict(mod_syms)
+        scope.update(ms)
         for u in units:
-            gen = Gen(u, typedefs, ms, all_units, rewrites, consts)
+            gen = Gen(u, typedefs, scope, all_units, rewrites, consts, interfaces)
+            # gfortran keeps the variables of a main program in static, zero-filled storage; by default this run-time fills
+            # them with NaN / a sentinel instead (visible), `static_zero_programs` reproduces the compiled behaviour
+            gen.zero_fill = static_zero_programs and u.kind == 'program'
             out.append(gen.gen_unit())
     for td in typedefs.values():
+        g = Gen(Unit('program', '_type'), typedefs, mod_syms, all_units, None, consts)
         out.append(f'class _T_{td.name}:')
         out.append('    def __init__(self):')
         for f_, t in td.fields.items():
-            out.append(f'        self.{mangle(f_)} = None')
+            init = td.inits.get(f_)
+            out.append(f'        self.{mangle(f_)} = {g.conv(t, parse_expr(init)) if init else None}')
         out.append('        pass')
         for p in td.procs:
+            dummies = all_units[p].args[1:] if p in all_units else []
             out.append(f'    def {mangle(p)}(self, *a):')
             out.append(f'        return {mangle(p)}(self, *a)')
         out.append(f'def _new_{td.name}():')

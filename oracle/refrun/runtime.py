@@ -11,12 +11,12 @@ import threading
 
 import numpy as np
 
-__all__ = ['np', '_assign', 'Ref', 'FortranStop', 'FortranExit', '_UNSET', '_f4', '_f8', '_idiv', '_div', '_pow', '_alloc', '_rt',
+__all__ = ['np', '_assign', '_cbind', '_AttrRef', 'set_clib', 'c_null_ptr', 'c_null_char', 'Ref', 'FortranStop', 'FortranExit', '_UNSET', '_f4', '_f8', '_idiv', '_div', '_pow', '_alloc', '_rt',
            'Runtime', 'INT_SENTINEL'] + [
     '_in_' + n for n in ('min', 'max', 'abs', 'sqrt', 'acos', 'asin', 'atan', 'cos', 'sin', 'tan', 'exp', 'log', 'dble',
                          'real', 'int', 'nint', 'mod', 'size', 'matmul', 'transpose', 'trim', 'adjustl', 'len_trim',
                          'iargc', 'command_argument_count', 'allocated', 'null', 'float', 'sum', 'dot_product',
-                         'sign', 'floor', 'ceiling', 'maxval', 'minval')]
+                         'sign', 'floor', 'ceiling', 'maxval', 'minval', 'present')]
 
 _f4 = np.float32
 _f8 = np.float64
@@ -82,7 +82,9 @@ def _pow(a, b):
     return np.power(a, b)
 
 
-def _alloc(typ, shape):
+def _alloc(typ, shape, zero=False):
+    if zero and typ in ('i', 'd', 'r'):
+        return np.zeros(shape, dtype={'i': np.int64, 'd': np.float64, 'r': np.float32}[typ], order='F')
     if typ == 'i':
         return np.full(shape, INT_SENTINEL, dtype=np.int64, order='F')
     if typ == 'd':
@@ -91,6 +93,8 @@ def _alloc(typ, shape):
         return np.full(shape, np.nan, dtype=np.float32, order='F')
     if typ == 'l':
         return np.zeros(shape, dtype=bool, order='F')
+    if typ == 'c':
+        return np.full(shape, b'?', dtype='S1', order='F')
     raise TypeError(f"array of type {typ!r}")
 
 
@@ -105,6 +109,90 @@ def _assign(dst, v):
         _rt.notes.append(f"non-conforming array assignment: {v.size} elements into {dst.size}")
     else:
         dst[...] = v
+
+
+# ---- ISO_C_BINDING: BIND(C) interface functions are bound to a shared library with ctypes -----------------------------
+
+c_null_ptr = None
+c_null_char = '\0'
+_CLIB = [None]
+
+
+def set_clib(lib):
+    """the shared library the BIND(C) interface functions resolve in (a ctypes.CDLL)."""
+    _CLIB[0] = lib
+
+
+class _AttrRef:
+    """a derived-type component passed by reference."""
+    __slots__ = ('o', 'a')
+
+    def __init__(self, o, a):
+        self.o, self.a = o, a
+
+    @property
+    def v(self):
+        return getattr(self.o, self.a)
+
+    @v.setter
+    def v(self, val):
+        setattr(self.o, self.a, val)
+
+
+def _cbind(name, spec, result):
+    """python callable for `<result> FUNCTION name(...) BIND(C)`; spec = [(type, VALUE?, array?)] per dummy.
+    Marshalling is what a Fortran processor does for these declarations: VALUE scalars by value (c_int / c_double /
+    void*), other scalars by address (copied back), arrays by address of contiguous column-major storage of the declared C
+    kind (INTEGER arrays of this run-time are 64-bit: converted to C_INT on the way in and copied back on the way out),
+    CHARACTER arrays / strings as char*."""
+    import ctypes as C
+
+    def call(*args):
+        lib = _CLIB[0]
+        if lib is None:
+            raise RuntimeError(f"{name}: no library bound (runtime.set_clib)")
+        fn = getattr(lib, name)
+        fn.restype = {'i': C.c_int, 'd': C.c_double, None: C.c_int}[result]
+        cargs, after = [], []
+        if len(args) != len(spec):
+            raise TypeError(f"{name}: {len(args)} arguments for {len(spec)} dummies")
+        for a, (typ, value, is_array) in zip(args, spec):
+            if value:
+                v = a.v if isinstance(a, (Ref, _AttrRef)) else a
+                cargs.append({'i': C.c_int, 'd': C.c_double, 'h': C.c_void_p}[typ](v if typ == 'h' else (int(v) if typ == 'i' else float(v))))
+            elif is_array:
+                if typ == 'c':
+                    raw = a.encode() if isinstance(a, str) else (np.asarray(a).tobytes() if a is not None else b'')
+                    buf = C.create_string_buffer(raw, max(len(raw), 1) + 1)
+                    cargs.append(buf)
+                elif a is None:
+                    cargs.append(None)
+                else:
+                    dt = np.int32 if typ == 'i' else np.float64
+                    arr = np.asarray(a)
+                    tmp = np.asfortranarray(arr, dtype=dt)
+                    cargs.append(tmp.ctypes.data_as(C.c_void_p))
+                    if tmp is not arr and not np.shares_memory(tmp, arr):
+                        after.append((arr, tmp))
+                    after.append((None, tmp))           # keep alive
+            else:
+                ct = {'i': C.c_int, 'd': C.c_double, 'h': C.c_void_p}[typ]
+                cur = a.v
+                box = ct() if cur is None else ct(cur if typ == 'h' else (int(cur) if typ == 'i' else float(cur)))
+                cargs.append(C.byref(box))
+                after.append((a, box))
+        rc = fn(*cargs)
+        for dst, src in after:
+            if dst is None:
+                continue
+            if isinstance(dst, np.ndarray):
+                dst[...] = src
+            else:
+                dst.v = src.value
+        return int(rc) if result in ('i', None) else np.float64(rc)
+
+    call.__name__ = name
+    return call
 
 
 # ---- intrinsics ---------------------------------------------------------------------------------------------------
@@ -221,6 +309,10 @@ def _in_allocated(a):
 
 def _in_null():
     return None
+
+
+def _in_present(a):
+    return a is not None
 
 
 def _in_trim(s):

@@ -168,3 +168,37 @@ def test_the_references_own_program_with_the_integration_diff_runs_on_the_librar
     assert np.array_equal(np.array([[r[0], r[1]] for r in rec]), g["temp_dat_index"])
     x = np.array([r[2] for r in rec])
     assert np.abs(x - g["temp_dat_value"]).max() <= 1e-4 * np.abs(g["temp_dat_value"]).max()
+
+
+def test_the_references_own_program_runs_on_the_library_through_the_fortran_module(gpu, tmp_path):
+    """As above, but Module_SolverB200 is include/pfem_b200.f90 ITSELF, translated and executed, its BIND(C) interfaces bound
+    to the real libpfemb200.so (the marshalling is checked against a C test double on the CPU in tests/test_refrun_dropin.py)."""
+    import ctypes
+    import gzip
+    from oracle.refrun import dropin
+    if not dropin.module_available():
+        pytest.skip("oracle/_ref/dropin_f90_tetrapoissonparallelimpl1.py was not built (no reference tree at build time)")
+    argv = []
+    for kind in ("nodes", "elems", "DirichBC"):
+        with gzip.open(os.path.join(GOLDEN, "input", f"tet10-{kind}.dat.gz")) as g_, open(tmp_path / f"tet10-{kind}.dat", "wb") as o:
+            o.write(g_.read())
+        argv.append(f"tet10-{kind}.dat")
+    lib = S.load_library()
+    c = {}
+
+    def capture(handle):                       # just before the PROGRAM's own `call solverpetsc%free()`
+        s = object.__new__(S.SolverB200)
+        s._lib, s._h, s.rank, s.nranks = lib, ctypes.c_void_p(handle), 0, 1
+        rp, col, val = s.get_csr()
+        c.update(rowptr=np.array(rp), col=np.array(col), val=np.array(val), rhs=np.array(s.get_rhs()), info=dict(s.info()))
+        s._h = ctypes.c_void_p()               # the handle stays the PROGRAM's to free
+
+    rt = dropin.run_through_module("tetrapoissonparallelimpl1.F", argv, lib, cwd=str(tmp_path), before_free=capture)
+    g = np.load(os.path.join(GOLDEN, "ref_driver_tet10_p1.npz"))
+    assert np.array_equal(c["rowptr"], g["rowptr"]) and np.array_equal(c["col"], g["col"])
+    assert np.array_equal(c["val"], g["val"]) and np.array_equal(c["rhs"], g["rhs"])
+    assert c["info"]["reason"] > 0 and c["info"]["its"] > 0
+    rec = rt.written["temp.dat"]
+    assert np.array_equal(np.array([[r[0], r[1]] for r in rec]), g["temp_dat_index"])
+    x = np.array([r[2] for r in rec])
+    assert np.abs(x - g["temp_dat_value"]).max() <= 1e-4 * np.abs(g["temp_dat_value"]).max()

@@ -109,3 +109,56 @@ def test_the_edit_anchors_guard_the_line_numbers():
     for kept in ("call solverpetsc%initialise(size_local, size_global,", "call solverpetsc%setZero()",
                  "call solverpetsc%factoriseAndSolve()", "call solverpetsc%free()", "write(1,*) ii, ind, fact"):
         assert kept in text, kept
+
+
+# ---- the same PROGRAM through the real Fortran module (include/pfem_b200.f90), against a C test double of the ABI ----------
+
+@pytest.fixture(scope="module")
+def fake_lib(tmp_path_factory):
+    import ctypes
+    import subprocess
+    d = tmp_path_factory.mktemp("fake_abi")
+    so = str(d / "libfakepfem.so")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fake_abi", "fake_pfem.c")
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-Wall", "-o", so, src], check=True)
+    lib = ctypes.CDLL(so)
+    lib.fake_last.restype = ctypes.c_void_p
+    lib.fake_scalar.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.fake_ints.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.fake_ints.restype = ctypes.POINTER(ctypes.c_int)
+    lib.fake_doubles.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.fake_doubles.restype = ctypes.POINTER(ctypes.c_double)
+    return lib
+
+
+def test_edited_program_through_the_fortran_module_marshals_the_abi_exactly(tmp_path, fake_lib):
+    """include/pfem_b200.f90 itself is executed (translated by oracle/refrun), its BIND(C) interfaces bound to a C test double
+    with the prototypes of include/pfem_b200.h: every scalar and array the reference's edited PROGRAM passes arrives as the C
+    side expects it (int32, SoA), in the order of INTEGRATION.md, and the PROGRAM's own temp.dat loop writes what
+    pfem_solver_get_solution returned."""
+    from oracle.refrun import dropin
+    argv = stage(tmp_path, "tet10")
+    seen = {}
+    rt = dropin.run_through_module("tetrapoissonparallelimpl1.F", argv, fake_lib, cwd=str(tmp_path),
+                                   before_free=lambda h: seen.setdefault("handle", h))
+    g = np.load(os.path.join(GOLDEN, "ref_driver_tet10_p1.npz"))
+    f = fake_lib.fake_last()
+    assert seen["handle"] == f
+    sc = [fake_lib.fake_scalar(f, k) for k in range(11)]
+    nElem, nNode, N = 6000, 1331, 729
+    assert sc[:10] == [0, 0, 1, N, N, 1, nElem, nNode, 4, nNode]       # device, rank, nranks, sizes, kind = PFEM_POISSON_TETRA ...
+    ints = lambda k, n: np.ctypeslib.as_array(fake_lib.fake_ints(f, k), shape=(n,)).copy()          # noqa: E731
+    dbls = lambda k, n: np.ctypeslib.as_array(fake_lib.fake_doubles(f, k), shape=(n,)).copy()       # noqa: E731
+    assert list(ints(5, sc[10])) == [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]    # create ... get_solution, free
+    assert set(ints(0, N)) == {50} and set(ints(1, N)) == {25}
+    from pfemfort_b200 import mesh as M
+    m = M.read_mesh(os.path.join(GOLDEN, "input", "tet10"))
+    assert np.array_equal(ints(2, 4 * nElem).reshape(4, nElem), m.conn)                    # SoA [npElem][nElem], one rank: new = old
+    assert np.array_equal(dbls(0, 3 * nNode).reshape(3, nNode), m.coords)
+    assert np.array_equal(ints(3, nNode), np.arange(1, nNode + 1))
+    assert np.array_equal(ints(4, 4 * nElem).reshape(4, nElem), g["ElemDofArray"].T)
+    assert np.array_equal(dbls(1, nNode), g["solnApplied"])
+    assert list(dbls(2, 8)) == [1.0, 1.0, 1.0, 0, 0, 0, 0, 0] and list(dbls(3, 8)) == [0, 1.0, 0, 0, 0, 0, 0, 0]
+    rec = rt.written["temp.dat"]
+    assert np.array_equal(np.array([[r[0], r[1]] for r in rec]), g["temp_dat_index"])
+    assert [r[2] for r in rec] == [1000.0 + i for i in range(N)]
