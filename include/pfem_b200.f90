@@ -8,9 +8,13 @@
 ! The element loop of the value pass (tetrapoissonparallelimpl1.F:828-884) becomes one call of
 ! solver%assemble(elemData, timeData); see INTEGRATION.md for the full diff of tetrapoissonparallelimpl1.F.
 !
-! NOTE: no Fortran compiler exists in the build image, so this file is kept deliberately thin (pure interface
-! blocks + one-line wrappers, names mirrored 1:1 from include/pfem_b200.h) and has not been compiled here.
-! Whoever has a toolchain: `gfortran -std=f2008 -fsyntax-only include/pfem_b200.f90` is the first check (INTEGRATION.md).
+! NOTE: no Fortran compiler exists in the build image, so this file is kept deliberately thin (pure interface blocks +
+! one-line wrappers, names mirrored 1:1 from include/pfem_b200.h) and has not been compiled.  What has been done instead:
+! it is parsed and EXECUTED by the Fortran front end of oracle/refrun (tests/test_fortran_module.py: every BIND(C) interface
+! is checked against the prototype of the same name in pfem_b200.h -- argument count, VALUE vs address, C kind -- and against
+! the symbols libpfemb200.so exports; tests/test_refrun_dropin.py: the reference's own tetrapoissonparallelimpl1.F with the
+! INTEGRATION.md diff runs through this module).  Whoever has a toolchain:
+! `gfortran -std=f2008 -fsyntax-only include/pfem_b200.f90` is still the first check (INTEGRATION.md).
       MODULE Module_SolverB200
       USE, INTRINSIC :: ISO_C_BINDING
       IMPLICIT NONE
