@@ -256,6 +256,92 @@ def make_explicit(path, steps=EXPLICIT_STEPS):
     return out
 
 
+# ---- TYPE PetscSolver's procedures (solverpetsc.F), driven by a small harness PROGRAM written here -------------------------
+
+SOLVER_HARNESS = """
+      PROGRAM SolverProcedures
+      USE Module_SolverPetsc
+      IMPLICIT NONE
+      TYPE(PetscSolver) :: s
+      PetscErrorCode errpetsc
+      INTEGER :: dn(6), on(6), e1(3), e2(3), e3(3), r2(3), c2(3), r3(3)
+      INTEGER :: ii, jj, mode
+      DOUBLE PRECISION :: Z(3,3), K1(3,3), K2(3,3), F1(3), F3(3)
+      CHARACTER(len=32) :: arg
+      CALL getarg(1, arg)
+      READ(arg,*) mode
+      call PetscInitialize("petsc_options.dat", errpetsc)
+      dn = 6; on = 6
+      call s%initialise(6, 6, dn, on)
+      IF(mode == 1) THEN
+        call s%factorise()
+      END IF
+      IF(mode == 2) THEN
+        call s%solve()
+      END IF
+!     pattern pass, as the drivers do it: zero blocks, INSERT_VALUES
+      e1(1) = 0; e1(2) = 1; e1(3) = 2
+      e2(1) = 2; e2(2) = 3; e2(3) = 4
+      e3(1) = 3; e3(2) = 4; e3(3) = 5
+      Z = 0.0
+      call MatSetValues(s%mtx, 3, e1, 3, e1, Z, INSERT_VALUES, errpetsc)
+      call MatSetValues(s%mtx, 3, e2, 3, e2, Z, INSERT_VALUES, errpetsc)
+      call MatSetValues(s%mtx, 3, e3, 3, e3, Z, INSERT_VALUES, errpetsc)
+      call s%setZero()
+      DO jj=1,3
+        DO ii=1,3
+          K1(ii,jj) = 10.0d0*ii + jj + 0.125d0
+          K2(ii,jj) = -1.0d0*ii + 100.0d0*jj + 0.5d0
+        END DO
+        F1(jj) = 7.0d0 + jj
+        F3(jj) = -3.0d0*jj
+      END DO
+      call s%assembleMatrixAndVector(e1, e1, K1, F1)
+      r2(1) = 2; r2(2) = -1; r2(3) = 4
+      c2(1) = 3; c2(2) = 4;  c2(3) = -1
+      call s%assembleMatrix(r2, c2, K2)
+      r3(1) = 5; r3(2) = -1; r3(3) = 3
+      call s%assembleVector(r3, F3)
+      call s%assembleMatrixAndVector(e3, e3, K2, F1)
+      call VecSetValue(s%rhsVec, 5, 1.5d0, ADD_VALUES, errpetsc)
+      call s%factoriseAndSolve()
+      call s%free()
+      END PROGRAM SolverProcedures
+"""
+
+
+def make_solver_procedures(path):
+    """solverpetsc.F's own procedures (initialise, setZero, assembleMatrix / Vector / MatrixAndVector, factorise, solve,
+    factoriseAndSolve) executed under the harness above: the Mat / Vec at KSPSolve, and where the state machine STOPs."""
+    import warnings
+    from oracle.refrun import fortran_to_py as F
+    from oracle.refrun import mocks
+    from oracle.refrun.runtime import Runtime, _rt
+    sources = R.read_sources(['solverpetsc.F'])
+    sources['harness.F'] = SOLVER_HARNESS
+    code = compile(F.translate(sources), '<solver harness>', 'exec')
+    out = {}
+    for mode in (0, 1, 2):
+        world = mocks.World(1)
+        _rt.bind(Runtime(['harness', str(mode)], '.', 0, world, True))
+        ns = dict(mocks.namespace())
+        exec(code, ns)
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                ns['program_solverprocedures']()
+            assert mode == 0
+            rowptr, col, val, rhs = world.system
+            out.update(rowptr=rowptr.astype(np.int32), col=col.astype(np.int32), val=val, rhs=rhs)
+        except FortranStop as ex:
+            assert mode in (1, 2)
+            out[f'stop_mode{mode}_line'] = np.int32(ex.line)
+            out[f'stop_mode{mode}_msg'] = np.array(ex.msg)
+    if path:
+        np.savez_compressed(path, **out)
+    return out
+
+
 # ---- the compiled mesh generator ----------------------------------------------------------------------------------------
 
 GENTETRA_GRIDS = {
@@ -295,5 +381,7 @@ if __name__ == '__main__':
     print('ref_elements.npz written')
     for tag in make_drivers(HERE):
         print('ref_driver_%s.npz written' % tag)
+    make_solver_procedures(os.path.join(HERE, 'ref_solver_procedures.npz'))
+    print('ref_solver_procedures.npz written')
     make_explicit(os.path.join(HERE, 'ref_explicit_cookmembranetria32.npz'))
     print('ref_explicit_cookmembranetria32.npz written')

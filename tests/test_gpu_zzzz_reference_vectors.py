@@ -202,3 +202,36 @@ def test_the_references_own_program_runs_on_the_library_through_the_fortran_modu
     assert np.array_equal(np.array([[r[0], r[1]] for r in rec]), g["temp_dat_index"])
     x = np.array([r[2] for r in rec])
     assert np.abs(x - g["temp_dat_value"]).max() <= 1e-4 * np.abs(g["temp_dat_value"]).max()
+
+
+def test_cuda_petscsolver_procedures_equal_the_executed_wrapper(gpu):
+    """TYPE PetscSolver's procedures as solverpetsc.F executes them (tests/golden/ref_solver_procedures.npz; the call sequence
+    is test_reference_vectors.solver_procedure_calls) against the library's mirrors: same matrix, same right-hand side,
+    PFEM_ERR_STATE where the reference STOPs."""
+    import test_reference_vectors as T
+    g = np.load(os.path.join(GOLDEN, "ref_solver_procedures.npz"))
+    seq = T.solver_procedure_calls()
+    s = S.SolverB200(0)
+    s.initialise(6, 6)
+    for bad in (s.factorise, s.solve):                       # out of order: the reference STOPs (:418, :444)
+        with pytest.raises(S.PfemError) as ei:
+            bad()
+        assert ei.value.status == S.ERR_STATE
+    edof = np.array(seq["pattern"], np.int32).T              # [nsize, nElem]
+    coords = np.array([[0.0, 1.0, 2.0, 0.0, 1.0, 2.0], [0.0, 0.0, 0.0, 1.0, 1.0, 1.5]])
+    s.set_mesh(S.POISSON_TRIA, edof + 1, coords)
+    s.set_pattern(edof)
+    s.setZero()
+    for c in seq["calls"]:
+        if c[0] == "mv":
+            s.assembleMatrixAndVector(c[1], c[2], c[3], c[4])
+        elif c[0] == "m":
+            s.assembleMatrix(c[1], c[2], c[3])
+        elif c[0] == "v":
+            s.assembleVector(c[1], c[4])
+        else:
+            s.add_value(c[1], c[2])
+    rp, col, val = s.get_csr()
+    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(col, g["col"])
+    assert np.array_equal(val, g["val"]) and np.array_equal(s.get_rhs(), g["rhs"])
+    s.free()

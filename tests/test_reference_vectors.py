@@ -221,6 +221,53 @@ def test_shipped_beam_file_stops_with_negative_jacobian():
     assert list(_driver("beam3Dtet6366", 1)["shipped_stop_line"]) == [321]
 
 
+# ---- TYPE PetscSolver's own procedures, executed ----------------------------------------------------------------
+
+def solver_procedure_calls():
+    """the call sequence of the harness PROGRAM in tests/golden/make_reference_vectors.py (SOLVER_HARNESS), as data."""
+    ii, jj = np.meshgrid(np.arange(1, 4), np.arange(1, 4), indexing="ij")
+    K1 = 10.0 * ii + jj + 0.125
+    K2 = -1.0 * ii + 100.0 * jj + 0.5
+    F1 = 7.0 + np.arange(1, 4)
+    F3 = -3.0 * np.arange(1, 4)
+    e1, e2, e3 = [0, 1, 2], [2, 3, 4], [3, 4, 5]
+    return dict(pattern=[e1, e2, e3], calls=[("mv", e1, e1, K1, F1), ("m", [2, -1, 4], [3, 4, -1], K2, None),
+                                             ("v", [5, -1, 3], None, None, F3), ("mv", e3, e3, K2, F1), ("value", 5, 1.5)])
+
+
+def test_petscsolver_procedures_as_executed():
+    """solverpetsc.F:328-401 executed: assembleMatrix / assembleVector / assembleMatrixAndVector add KLOCAL(ii,jj) at
+    (R(ii), C(jj)) -- NOT transposed, unlike the drivers' direct MatSetValues --, negative indices are skipped, and the state
+    machine STOPs in factorise (:418) / solve (:444) when called out of order."""
+    g = np.load(os.path.join(GOLDEN, "ref_solver_procedures.npz"))
+    seq = solver_procedure_calls()
+    A, b = np.zeros((6, 6)), np.zeros(6)
+    patt = np.zeros((6, 6), bool)
+    for e in seq["pattern"]:
+        patt[np.ix_(e, e)] = True
+    for c in seq["calls"]:
+        if c[0] == "value":
+            b[c[1]] += c[2]
+            continue
+        kind, r, cc, K, F = c
+        for i, ri in enumerate(r):
+            if ri < 0:
+                continue
+            if F is not None:
+                b[ri] += F[i]
+            if K is not None:
+                for j, cj in enumerate(cc):
+                    if cj >= 0:
+                        assert patt[ri, cj]
+                        A[ri, cj] += K[i, j]
+    rp, col = g["rowptr"], g["col"]
+    rows = np.repeat(np.arange(6), np.diff(rp))
+    assert np.array_equal(np.flatnonzero(patt.ravel()), rows * 6 + col)
+    assert np.array_equal(A[rows, col], g["val"]) and np.array_equal(b, g["rhs"])
+    assert int(g["stop_mode1_line"]) == 418 and "solverpetsc->factorise" in str(g["stop_mode1_msg"])
+    assert int(g["stop_mode2_line"]) == 444 and "solverpetsc->solve" in str(g["stop_mode2_msg"])
+
+
 # ---- explicit dynamics (SURVEY 8 f3): the reference's central-difference PROGRAM, executed --------------------------------
 
 def test_oracle_explicit_time_loop_equals_the_executed_program(input_dir):
@@ -306,6 +353,10 @@ def test_regenerated_vectors_equal_the_committed_files(tmp_path):
     assert set(new) == set(old.files)
     for k in old.files:
         assert np.array_equal(new[k], old[k]), k
+    new = gen.make_solver_procedures(None)
+    old = np.load(os.path.join(GOLDEN, "ref_solver_procedures.npz"))
+    for k in old.files:
+        assert np.array_equal(np.asarray(new[k]), old[k]), k
     new = gen.make_explicit(None, steps=3)
     old = np.load(os.path.join(GOLDEN, "ref_explicit_cookmembranetria32.npz"))
     assert np.array_equal(new["globalM"], old["globalM"]) and np.array_equal(new["solnoutput"], old["solnoutput"][:3])
