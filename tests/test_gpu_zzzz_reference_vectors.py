@@ -161,15 +161,23 @@ def test_cuda_petscsolver_procedures_equal_the_executed_wrapper(gpu):
     g = np.load(os.path.join(GOLDEN, "ref_solver_procedures.npz"))
     seq = T.solver_procedure_calls()
     s = S.SolverB200(0)
-    s.initialise(6, 6)
+    s.initialise(729, 729)
     for bad in (s.factorise, s.solve):                       # out of order: the reference STOPs (:418, :444)
         with pytest.raises(S.PfemError) as ei:
             bad()
         assert ei.value.status == S.ERR_STATE
-    edof = np.array(seq["pattern"], np.int32).T              # [nsize, nElem]
-    coords = np.array([[0.0, 1.0, 2.0, 0.0, 1.0, 2.0], [0.0, 0.0, 0.0, 1.0, 1.0, 1.5]])
-    s.set_mesh(S.POISSON_TRIA, edof + 1, coords)
-    s.set_pattern(edof)
+    # rows 0..5 carry the harness's three index sets; a 20 x 20 triangle grid (all dofs free) follows on rows 6.., so that the
+    # pattern pass runs at the size of the bundled fixtures
+    grid = M.gen_tria_poisson(20)
+    special = np.array(seq["pattern"], np.int32).T           # [nsize, 3 elements], dofs = nodes - 1
+    conn = np.concatenate([special + 1, grid.conn + 6], axis=1).astype(np.int32)
+    coords = np.concatenate([np.array([[0.0, 1.0, 2.0, 0.0, 1.0, 2.0], [0.0, 0.0, 0.0, 1.0, 1.0, 1.5]]), grid.coords + 10.0], axis=1)
+    N = coords.shape[1]
+    s.free()
+    s = S.SolverB200(0)
+    s.initialise(N, N)
+    s.set_mesh(S.POISSON_TRIA, conn, coords)
+    s.set_pattern(conn - 1)
     s.setZero()
     for c in seq["calls"]:
         if c[0] == "mv":
@@ -181,8 +189,10 @@ def test_cuda_petscsolver_procedures_equal_the_executed_wrapper(gpu):
         else:
             s.add_value(c[1], c[2])
     rp, col, val = s.get_csr()
-    assert np.array_equal(rp, g["rowptr"]) and np.array_equal(col, g["col"])
-    assert np.array_equal(val, g["val"]) and np.array_equal(s.get_rhs(), g["rhs"])
+    k = g["rowptr"][-1]
+    assert np.array_equal(rp[:7], g["rowptr"]) and np.array_equal(col[:k], g["col"])
+    assert np.array_equal(val[:k], g["val"]) and np.array_equal(s.get_rhs()[:6], g["rhs"])
+    assert not val[k:].any() and not s.get_rhs()[6:].any()
     s.free()
 
 
