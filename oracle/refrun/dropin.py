@@ -49,12 +49,40 @@ EDITS = {
         (968, 968, ["      DEALLOCATE(soln_b200)"]),
     ],
 }
+# the 3-D elasticity driver: the same edits, plus the ForceBC loop with VecSetValue -> pfem_solver_add_value
+EDITS['tetraelasticityparallelimpl1.F'] = [
+    (24, 24, ["      USE Module_SolverB200"]),
+    (111, 111, ["      TYPE(B200Solver) :: solverpetsc",
+                "      DOUBLE PRECISION, DIMENSION(:), ALLOCATABLE :: soln_b200",
+                "      INTEGER :: ierr"]),
+    (174, 174, ["      call MPI_Comm_rank(PETSC_COMM_WORLD, this_mpi_proc, errpetsc);",
+                "      call solverpetsc%create(0, this_mpi_proc, n_mpi_procs)"]),
+    (862, 874, ["      ierr = pfem_solver_set_mesh(solverpetsc%h, PFEM_ELASTICITY_TETRA,",
+                "     1   nElem_global, elemNodeConn, nNode_global, coords,",
+                "     2   node_map_get_old)",
+                "      ierr = pfem_solver_set_pattern(solverpetsc%h, nElem_global,",
+                "     1   nsize, ElemDofArray)"]),
+    (906, 965, ["      ierr = pfem_solver_set_applied(solverpetsc%h, solnApplied,",
+                "     1   nNode_global*ndof)",
+                "      call solverpetsc%assemble(elemData, timeData)"]),
+    (979, 980, ["        ierr = pfem_solver_add_value(solverpetsc%h, row, fact)"]),
+    (1019, 1029, ["      ALLOCATE(soln_b200(ntotdofs_global))",
+                  "      ierr = pfem_solver_get_solution(solverpetsc%h, soln_b200)"]),
+    (1035, 1035, ["          fact = soln_b200(ii)"]),
+    (1077, 1077, ["      DEALLOCATE(soln_b200)"]),
+]
+
 # what the edited lines must contain today (the reference tree is read-only; this guards the line numbers)
 ANCHORS = {
     'tetrapoissonparallelimpl1.F': {26: 'USE Module_SolverPetsc', 107: 'TYPE(PetscSolver) :: solverpetsc',
                                     175: 'MPI_Comm_rank', 791: 'LoopElem: DO ee=1, nElem_global', 802: 'END DO LoopElem',
                                     828: 'DO ee=1, nElem_global', 884: 'END DO', 922: 'VecScatterCreateToAll',
                                     932: 'VecGetArray', 938: 'fact = xx_v(xx_i+ii)', 968: 'VecRestoreArray'},
+    'tetraelasticityparallelimpl1.F': {24: 'USE Module_SolverPetsc', 111: 'TYPE(PetscSolver) :: solverpetsc',
+                                       174: 'MPI_Comm_rank', 862: 'LoopElem: DO ee=1, nElem_global', 874: 'END DO LoopElem',
+                                       906: 'DO ee=1, nElem_global', 965: 'END DO', 979: 'call VecSetValue(solverpetsc%rhsVec, row, fact',
+                                       980: 'ADD_VALUES, errpetsc)', 1019: 'VecScatterCreateToAll', 1029: 'VecGetArray',
+                                       1035: 'fact = xx_v(xx_i+ii)', 1077: 'VecRestoreArray'},
 }
 
 

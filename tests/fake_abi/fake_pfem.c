@@ -7,6 +7,7 @@
 
 typedef struct {
     int device, rank, nranks, size_local, size_global, kind, nElem, nNode, nsize, n_applied, calls[16], ncalls;
+    int n_added, added_row[64]; double added_val[64];
     int *diag_nnz, *offdiag_nnz, *conn, *old, *edof;
     double *coords, *applied, elemData[8], timeData[8];
 } fake_t;
@@ -39,13 +40,18 @@ int pfem_solver_set_applied(fake_t *f, const double *a, int n) { f->n_applied = 
 int pfem_solver_assemble(fake_t *f, const double *ed, const double *td, int *nneg) {
     memcpy(f->elemData, ed, sizeof f->elemData); memcpy(f->timeData, td, sizeof f->timeData); *nneg = 0; note(f, 7); return 0;
 }
+int pfem_solver_add_value(fake_t *f, int row, double val) {
+    if (f->n_added < 64) { f->added_row[f->n_added] = row; f->added_val[f->n_added] = val; }
+    f->n_added++; return 0;
+}
 int pfem_solver_factorise_and_solve(fake_t *f) { note(f, 8); return 0; }
 int pfem_solver_get_solution(fake_t *f, double *x) { for (int i = 0; i < f->size_global; i++) x[i] = 1000.0 + i; note(f, 9); return 0; }
 int pfem_solver_free(fake_t *f) { note(f, 10); return 0; }   /* kept alive for the test to read */
 fake_t *fake_last(void) { return last; }
 int fake_scalar(fake_t *f, int which) {
-    int v[] = {f->device, f->rank, f->nranks, f->size_local, f->size_global, f->kind, f->nElem, f->nNode, f->nsize, f->n_applied, f->ncalls};
+    int v[] = {f->device, f->rank, f->nranks, f->size_local, f->size_global, f->kind, f->nElem, f->nNode, f->nsize, f->n_applied, f->ncalls,
+               f->n_added};
     return v[which];
 }
-const int *fake_ints(fake_t *f, int which) { const int *p[] = {f->diag_nnz, f->offdiag_nnz, f->conn, f->old, f->edof, f->calls}; return p[which]; }
-const double *fake_doubles(fake_t *f, int which) { const double *p[] = {f->coords, f->applied, f->elemData, f->timeData}; return p[which]; }
+const int *fake_ints(fake_t *f, int which) { const int *p[] = {f->diag_nnz, f->offdiag_nnz, f->conn, f->old, f->edof, f->calls, f->added_row}; return p[which]; }
+const double *fake_doubles(fake_t *f, int which) { const double *p[] = {f->coords, f->applied, f->elemData, f->timeData, f->added_val}; return p[which]; }

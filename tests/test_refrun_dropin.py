@@ -72,11 +72,11 @@ class OracleBackedSolver:
         self.calls.append("free")
 
 
-def stage(tmp_path, prefix):
-    for kind in ("nodes", "elems", "DirichBC"):
+def stage(tmp_path, prefix, kinds=("nodes", "elems", "DirichBC")):
+    for kind in kinds:
         with gzip.open(os.path.join(GOLDEN, "input", f"{prefix}-{kind}.dat.gz")) as g, open(tmp_path / f"{prefix}-{kind}.dat", "wb") as o:
             o.write(g.read())
-    return [f"{prefix}-{kind}.dat" for kind in ("nodes", "elems", "DirichBC")]
+    return [f"{prefix}-{kind}.dat" for kind in kinds]
 
 
 def test_edited_reference_program_runs_against_the_solver_interface(tmp_path):
@@ -162,3 +162,35 @@ def test_edited_program_through_the_fortran_module_marshals_the_abi_exactly(tmp_
     rec = rt.written["temp.dat"]
     assert np.array_equal(np.array([[r[0], r[1]] for r in rec]), g["temp_dat_index"])
     assert [r[2] for r in rec] == [1000.0 + i for i in range(N)]
+
+
+def test_edited_elasticity_program_with_its_forcebc_loop(tmp_path, fake_lib):
+    """tetraelasticityparallelimpl1.F with the same diff: ndof = 3, the driver's own material constants, and its ForceBC loop
+    kept as is with VecSetValue replaced by pfem_solver_add_value -- rows and values as the unedited PROGRAM
+    adds them (the reference's node-based row formula and 0- / 1-based range test included)."""
+    from oracle.refrun import dropin
+    from pfemfort_b200 import driver as D, mesh as M, solver as S
+    argv = stage(tmp_path, "beam3Dtet6366", ("nodes", "elems", "DirichBC", "ForceBC"))
+    # documented-intent input: local nodes 3 <-> 4 (the shipped file has negative Jacobians)
+    lines = [l.split() for l in open(tmp_path / argv[1]) if l.strip()]
+    with open(tmp_path / argv[1], "w") as f:
+        for t in lines:
+            f.write(f"{t[0]} {t[1]} {t[2]} {t[4]} {t[3]}\n")
+    rt = dropin.run_through_module("tetraelasticityparallelimpl1.F", argv, fake_lib, cwd=str(tmp_path))
+    g = np.load(os.path.join(GOLDEN, "ref_driver_beam3Dtet6366_p1.npz"))
+    f = fake_lib.fake_last()
+    sc = [fake_lib.fake_scalar(f, k) for k in range(12)]
+    m = M.read_mesh(os.path.join(GOLDEN, "input", "beam3Dtet6366"), swap_34=True)
+    N = g["rowptr"].size - 1
+    assert sc[3:10] == [N, N, 3, m.nElem, m.nNode, 12, 3 * m.nNode]                 # kind = PFEM_ELASTICITY_TETRA, nsize = 12
+    ints = lambda k, n: np.ctypeslib.as_array(fake_lib.fake_ints(f, k), shape=(n,)).copy()          # noqa: E731
+    dbls = lambda k, n: np.ctypeslib.as_array(fake_lib.fake_doubles(f, k), shape=(n,)).copy()       # noqa: E731
+    assert np.array_equal(ints(2, 4 * m.nElem).reshape(4, m.nElem), m.conn)
+    assert np.array_equal(ints(4, 12 * m.nElem).reshape(12, m.nElem), g["ElemDofArray"].T)
+    assert np.array_equal(dbls(1, 3 * m.nNode), g["solnApplied"])
+    assert list(dbls(2, 8)[:6]) == D.DEFAULT_ELEMDATA[S.ELASTICITY_TETRA]           # 240.565, 0.3, 1.0, 0.1, 0, 0 as single literals
+    # the ForceBC adds = what driver.force_bc_rows hands to add_value on one rank
+    num = D.number(m, S.ELASTICITY_TETRA)
+    rows, vals = D.force_bc_rows(m, num, 3)
+    assert sc[11] == len(rows) > 0
+    assert list(ints(6, sc[11])) == list(rows) and list(dbls(4, sc[11])) == list(vals)
