@@ -37,6 +37,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 RTOL = 1e-10
+# what holds the oracle itself to the reference
+ORACLE_PIN = ("golden vectors from EXECUTING the reference's own Fortran (oracle/refrun; tests/golden/ref_*.npz): element routines, "
+              "numbering, pattern, assembled matrix / RHS bit for bit; PETSc's Krylov iterates are not pinned by a reference run")
 TUNING_ENV = ("PFEM_ASM", "PFEM_CG", "PFEM_CG_SR", "PFEM_PCG_CFG", "PFEM_PCG_FUSED", "PFEM_KERNELS_P2P", "PFEM_TILE_ROWS",
               "PFEM_TILE_THREADS", "PFEM_SYNC", "PFEM_ARITH", "PFEM_PCG_SYNC", "PFEM_PCG_HALO")
 
@@ -563,6 +566,8 @@ def main():
         "setup_s": t_setup, "clocks": clocks,
     }
     if parity is not None:
+        if isinstance(parity, dict):
+            parity.setdefault("oracle_pinned_by", ORACLE_PIN)
         line["parity"] = parity
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload, and the parity record ----
@@ -596,7 +601,7 @@ def main():
             par = {"oracle": f"OpenMP element loop, {threads} threads (unordered adds: agreement to rounding is the claim)",
                    "its_gpu": int(info["its"]), "its_oracle": (int(oits) if not its_cap else None),
                    "reason_gpu": int(info["reason"]), "reason_oracle": (int(oreason) if not its_cap else None),
-                   "tolerance": 1e-12}
+                   "tolerance": 1e-12, "oracle_pinned_by": ORACLE_PIN}
             if ne == m.nElem:
                 dv, nv = diff_stats(val, v2)
                 dr, nr = diff_stats(rhs, r2)
