@@ -218,7 +218,7 @@ int main(int argc, char **argv)
     }
     std::vector<double> x(size_global > 0 ? size_global : 1);
     CHECK(pfem_solver_get_solution(solver, x.data()));
-    if (rank == 0) {                                               // temp.dat: "ii  node  value" (:934-942)
+    if (rank == 0) {                                               // temp.dat as the PROGRAMs write it (:934-942)
         std::vector<int> assy(size_global);
         int count = 0;
         for (int n = 0; n < nNode; n++)
@@ -228,7 +228,8 @@ int main(int argc, char **argv)
         for (int ii = 0; ii < size_global; ii++) {
             const int slot = assy[ii] - 1, node_new = slot / ndof, d = slot % ndof;
             const int ind = (map_old[node_new] - 1) * ndof + d + 1;
-            fprintf(f, "%d %d %.17g\n", ii + 1, ind, x[ii]);
+            if (ndof == 1) fprintf(f, "%d %d %.17g\n", ii + 1, ind, x[ii]);   // write(1,*) ii, ind, fact   (tetrapoissonparallelimpl1.F:940)
+            else           fprintf(f, "%.17g\n", x[ii]);                      // write(1,*) fact            (tetraelasticityparallelimpl1.F:1046)
         }
         fclose(f);
         printf(" Program is successful \n");

@@ -54,12 +54,20 @@ def test_cpp_driver_single_rank(gpu, input_dir, tmp_path, name, phys, kind):
     assert f"Convergence in {oits} iterations." in r.stdout or f"Convergence in {oits + 1} iterations." in r.stdout \
         or f"Convergence in {oits - 1} iterations." in r.stdout, r.stdout
     t = np.loadtxt(os.path.join(str(tmp_path), "temp.dat"))
-    assert t.shape[0] == num.size_global
-    assert np.abs(t[:, 2] - ox).max() <= 1e-7 * np.abs(ox).max()
-    # the second column is the (old-numbering) node slot of every free dof, like assyForSoln
     npe, ndof, ndim = S.KIND_DIMS[kind]
-    free = np.flatnonzero(num.NodeDofArrayNew.T.ravel() > 0) + 1
-    assert np.array_equal(t[:, 1].astype(int), free)
+    # the Poisson PROGRAMs write "ii  node  value" (tetrapoissonparallelimpl1.F:940), the elasticity PROGRAMs the value only
+    # (tetraelasticityparallelimpl1.F:1046)
+    assert t.ndim == (2 if ndof == 1 else 1) and t.shape[0] == num.size_global
+    vals = t[:, 2] if ndof == 1 else t
+    assert np.abs(vals - ox).max() <= 1e-7 * np.abs(ox).max()
+    # ... and against the temp.dat records of the reference's own PROGRAM executed on the same files (tests/golden/ref_driver_*)
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_driver_{name}_p1.npz"))
+    assert np.abs(vals - g["temp_dat_value"]).max() <= 1e-8 * np.abs(g["temp_dat_value"]).max()
+    if ndof == 1:
+        # the second column is the (old-numbering) node slot of every free dof, like assyForSoln
+        free = np.flatnonzero(num.NodeDofArrayNew.T.ravel() > 0) + 1
+        assert np.array_equal(t[:, 1].astype(int), free)
+        assert np.array_equal(t[:, :2].astype(int), g["temp_dat_index"])
 
 
 def test_cpp_driver_two_ranks(gpu, input_dir, tmp_path):
