@@ -147,7 +147,7 @@ def test_cuda_explicit_time_loop_equals_the_executed_program(gpu, input_dir):
     ex.free()
 
 
-# ---- written after this round's GPU budget was spent (first run: the driver's round-end suite); kept last ------------------
+# ---- the last four (added late in round 2; run on the B200 in the round's last GPU call, profiles/r02_pytest_gpu_reference_vectors.log)
 
 def test_cuda_numbering_equals_the_executed_p_rank_driver_beam(gpu, input_dir):
     _numbering_against_the_executed_driver(input_dir, "beam3Dtet6366", 2)
