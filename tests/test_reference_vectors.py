@@ -343,6 +343,72 @@ def test_oracle_against_a_live_run_of_the_reference_routines(kind):
 
 
 @pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
+def test_oracle_and_host_numbering_against_live_runs_of_the_driver_on_random_small_cases(tmp_path):
+    """24 random tiny boxes (1-3 cells per axis), random Dirichlet sets WITH duplicate rows, 1-4 ranks with a random node
+    partition -- every fourth case with one rank that owns Dirichlet nodes only (size_local = 0) -- through the executed
+    tetrapoissonparallelimpl1.F, against the oracle and the product's host numbering: integers and pattern bit for bit,
+    values bit for bit on one rank and to 1e-12 on P."""
+    from oracle.refrun import run_reference as R
+    empty_rank_cases = multi = dup = 0
+    for seed in range(24):
+        rng = np.random.default_rng(100 + seed)
+        n = rng.integers(1, 4, 3)
+        m = M.gen_tetra(0, 1, int(n[0]), 0, 1.5, int(n[1]), -1, 1, int(n[2]))
+        nNode = m.nNode
+        p = min(int(rng.integers(1, 5)), nNode)
+        npid = rng.integers(0, p, nNode)
+        npid[:p] = np.arange(p)
+        dn = rng.integers(1, nNode + 1, int(rng.integers(1, nNode)))
+        if seed % 4 == 3 and p > 1:                       # every node of the last rank is a Dirichlet node
+            dn = np.concatenate([dn, np.flatnonzero(npid == p - 1) + 1])
+        if len(set(dn)) == nNode:
+            dn = dn[dn != dn[0]]
+        dv = np.round(rng.standard_normal(dn.size), 6)
+        d = tmp_path / f"case{seed}"
+        d.mkdir()
+        with open(d / "n.dat", "w") as f:
+            for i in range(nNode):
+                f.write(f"{i + 1}\t{m.coords[0, i]:.8f}\t{m.coords[1, i]:.8f}\t{m.coords[2, i]:.8f}\n")
+        with open(d / "e.dat", "w") as f:
+            for e in range(m.nElem):
+                f.write(f"{e + 1}\t" + "\t".join(str(x) for x in m.conn[:, e]) + "\n")
+        with open(d / "d.dat", "w") as f:
+            for a, b in zip(dn, dv):
+                f.write(f"{a}\t1\t{b:.8f}\n")
+        res = R.run_driver("tetrapoissonparallelimpl1.F", ["n.dat", "e.dat", "d.dat"], p,
+                           partition=(npid[m.conn[0] - 1], npid) if p > 1 else None, cwd=str(d))
+        assert res.stopped is None, (seed, res.stopped)
+        fa = res.ranks[0].final_arrays
+        info = np.array([[rt.final_locals[k] for k in ("node_start", "node_end", "row_start", "row_end", "size_local")]
+                         for rt in res.ranks])
+        mm = M.Mesh(m.coords, m.conn, dn.astype(np.int32), np.ones(dn.size, np.int32), dv.copy(), name="random")
+        part = npid if p > 1 else None
+        o = O.number_dofs(nNode, 1, mm.dbc_node, mm.dbc_dof, mm.dbc_val, p, part)
+        num = D.number(mm, S.POISSON_TETRA, p, part)
+        for got in (o["NodeDofArrayNew"], num.NodeDofArrayNew):
+            assert np.array_equal(got.T, fa["nodedofarraynew"]), seed
+        assert np.array_equal(o["node_map_get_old"], fa["node_map_get_old"]) and np.array_equal(num.node_map_get_old, fa["node_map_get_old"])
+        assert np.array_equal(o["solnApplied"], fa["solnapplied"]) and np.array_equal(num.solnApplied, fa["solnapplied"]), seed
+        assert np.array_equal(num.elemDof.T, fa["elemdofarray"]), seed
+        assert np.array_equal(num.part_info[:, [0, 1, 4]], info[:, [0, 1, 4]]), seed
+        own = info[:, 4] > 0
+        assert np.array_equal(num.part_info[own][:, [2, 3]], info[own][:, [2, 3]]), seed
+        rp, col = O.pattern(num.elemDof, o["size_global"])
+        val, rhs, nbad = O.assemble(S.POISSON_TETRA, num.conn_new, mm.coords, num.node_map_get_old, num.elemDof, num.solnApplied,
+                                    D.DEFAULT_ELEMDATA[S.POISSON_TETRA], D.DEFAULT_TIMEDATA, rp, col)
+        grp, gcol, gval, grhs = res.system
+        assert nbad == 0 and np.array_equal(rp, grp) and np.array_equal(col, gcol), seed
+        if p == 1:
+            assert np.array_equal(val, gval) and np.array_equal(rhs, grhs), seed
+        else:
+            assert P.values_within(grp, val, gval, 1e-12) and P.vector_within(rhs, grhs, 1e-12), seed
+        multi += p > 1
+        empty_rank_cases += bool((info[:, 4] == 0).any())
+        dup += dn.size > len(set(dn))
+    assert multi >= 10 and empty_rank_cases >= 2 and dup >= 10
+
+
+@pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
 def test_regenerated_vectors_equal_the_committed_files(tmp_path):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(GOLDEN, "make_reference_vectors.py"))
