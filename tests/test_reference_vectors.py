@@ -409,6 +409,76 @@ def test_oracle_and_host_numbering_against_live_runs_of_the_driver_on_random_sma
 
 
 @pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
+def test_forcebc_rows_against_live_runs_of_the_elasticity_driver_on_random_small_cases(tmp_path):
+    """16 random tiny clamped boxes, extra single-dof Dirichlet rows, random ForceBC rows, 1-3 ranks, through the executed
+    tetraelasticityparallelimpl1.F: the reference's node-based ForceBC row formula with its 0- vs 1-based range test adds
+    every row in 1..N-1 exactly once over all ranks and never row 0 -- what oracle.add_force_bc and driver.force_bc_rows
+    do.  A ForceBC row equal to N passes the reference's range test and PETSc then refuses it (index out of range): the
+    reference run dies there; oracle and host drop that row (documented deviation)."""
+    from oracle.refrun import run_reference as R
+    died = compared = 0
+    for seed in range(16):
+        rng = np.random.default_rng(500 + seed)
+        n = rng.integers(1, 4, 3)
+        m = M.gen_tetra(0, 1, int(n[0]), 0, 1.5, int(n[1]), -1, 1, int(n[2]), dbc="clamp_y0", ndof=3)
+        nNode = m.nNode
+        k = int(rng.integers(0, 6))
+        dn = np.concatenate([m.dbc_node, rng.integers(1, nNode + 1, k)])
+        dd = np.concatenate([m.dbc_dof, rng.integers(1, 4, k)])
+        dv = np.concatenate([m.dbc_val, np.round(rng.standard_normal(k), 5)])
+        nf = int(rng.integers(1, 6))
+        fn, fd, fv = rng.integers(1, nNode + 1, nf), rng.integers(1, 4, nf), np.round(rng.standard_normal(nf), 4)
+        p = min(int(rng.integers(1, 4)), nNode)
+        npid = rng.integers(0, p, nNode)
+        npid[:p] = np.arange(p)
+        d = tmp_path / f"case{seed}"
+        d.mkdir()
+        with open(d / "n.dat", "w") as f:
+            for i in range(nNode):
+                f.write(f"{i + 1}\t{m.coords[0, i]:.8f}\t{m.coords[1, i]:.8f}\t{m.coords[2, i]:.8f}\n")
+        with open(d / "e.dat", "w") as f:
+            for e in range(m.nElem):
+                f.write(f"{e + 1}\t" + "\t".join(str(x) for x in m.conn[:, e]) + "\n")
+        with open(d / "d.dat", "w") as f:
+            for a, b, c in zip(dn, dd, dv):
+                f.write(f"{a}\t{b}\t{c:.8f}\n")
+        with open(d / "f.dat", "w") as f:
+            for a, b, c in zip(fn, fd, fv):
+                f.write(f"{a}\t{b}\t{c:.8f}\n")
+        mm = M.Mesh(m.coords, m.conn, dn.astype(np.int32), dd.astype(np.int32), dv.copy(), name="random")
+        mm.fbc_node, mm.fbc_dof, mm.fbc_val = fn.astype(np.int32), fd.astype(np.int32), fv.copy()
+        part = npid if p > 1 else None
+        num = D.number(mm, S.ELASTICITY_TETRA, p, part)
+        hits_n = any((int(num.node_map_get_new[a - 1]) - 1) * 3 + int(b) - 1 == num.size_global for a, b in zip(fn, fd))
+        try:
+            res = R.run_driver("tetraelasticityparallelimpl1.F", ["n.dat", "e.dat", "d.dat", "f.dat"], p,
+                               partition=(npid[m.conn[0] - 1], npid) if p > 1 else None, cwd=str(d))
+        except IndexError as ex:
+            assert hits_n and "out of range" in str(ex), seed
+            died += 1
+            continue
+        assert not hits_n and res.stopped is None, seed
+        fa = res.ranks[0].final_arrays
+        assert np.array_equal(num.NodeDofArrayNew.T, fa["nodedofarraynew"]) and np.array_equal(num.elemDof.T, fa["elemdofarray"]), seed
+        rp, col = O.pattern(num.elemDof, num.size_global)
+        val, rhs, nbad = O.assemble(S.ELASTICITY_TETRA, num.conn_new, mm.coords, num.node_map_get_old, num.elemDof, num.solnApplied,
+                                    D.DEFAULT_ELEMDATA[S.ELASTICITY_TETRA], D.DEFAULT_TIMEDATA, rp, col)
+        rhs_host = rhs.copy()
+        O.add_force_bc(rhs, mm.fbc_node, mm.fbc_dof, mm.fbc_val, 3, num.node_map_get_new, num.NodeDofArrayNew, num.size_global)
+        for r, v in zip(*D.force_bc_rows(mm, num, 3)):
+            rhs_host[r] += v
+        grp, gcol, gval, grhs = res.system
+        assert np.array_equal(rp, grp) and np.array_equal(col, gcol), seed
+        if p == 1:
+            assert np.array_equal(val, gval) and np.array_equal(rhs, grhs) and np.array_equal(rhs_host, grhs), seed
+        else:
+            assert P.values_within(grp, val, gval, 1e-12) and P.vector_within(rhs, grhs, 1e-12), seed
+            assert P.vector_within(rhs_host, grhs, 1e-12), seed
+        compared += 1
+    assert compared >= 12 and died >= 1
+
+
+@pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
 def test_regenerated_vectors_equal_the_committed_files(tmp_path):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(GOLDEN, "make_reference_vectors.py"))
