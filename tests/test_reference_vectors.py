@@ -479,6 +479,58 @@ def test_forcebc_rows_against_live_runs_of_the_elasticity_driver_on_random_small
 
 
 @pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
+@pytest.mark.parametrize("driver,kind", [("triapoissonparallelimpl1.F", S.POISSON_TRIA), ("triaelasticityparallelimpl1.F", S.ELASTICITY_TRIA)])
+def test_triangle_drivers_live_on_random_small_cases(tmp_path, driver, kind):
+    """10 random small triangle grids per driver, random single-dof Dirichlet rows with NON-ZERO values (the lifting term of the
+    2-D elasticity driver, solnApplied(elemDofGlobal(ii)), is otherwise only exercised with zeros), 1-3 ranks, through the
+    executed tria drivers: numbering, pattern, matrix and right-hand side against the oracle."""
+    from oracle.refrun import run_reference as R
+    npe, ndof, ndim = S.KIND_DIMS[kind]
+    for seed in range(10):
+        rng = np.random.default_rng(900 + seed + 50 * kind)
+        g0 = M.gen_tria_poisson(int(rng.integers(2, 6)))
+        nNode = g0.nNode
+        coords = g0.coords + 0.02 * np.round(rng.standard_normal(g0.coords.shape), 3)      # keeps every Jacobian positive
+        k = int(rng.integers(2, max(3, nNode // 2)))
+        dn, dd = rng.integers(1, nNode + 1, k), rng.integers(1, ndof + 1, k)
+        dv = np.round(rng.standard_normal(k), 5)
+        if kind == S.ELASTICITY_TRIA:                      # pin one node completely (no rigid-body mode for the mock's solve)
+            dn, dd, dv = np.concatenate([dn, [1, 1, 2]]), np.concatenate([dd, [1, 2, 2]]), np.concatenate([dv, [0.0, 0.0, 0.0]])
+        p = min(int(rng.integers(1, 4)), nNode)
+        npid = rng.integers(0, p, nNode)
+        npid[:p] = np.arange(p)
+        d = tmp_path / f"case{seed}"
+        d.mkdir()
+        with open(d / "n.dat", "w") as f:
+            for i in range(nNode):
+                f.write(f"{i + 1}\t{coords[0, i]:.8f}\t{coords[1, i]:.8f}\n")
+        with open(d / "e.dat", "w") as f:
+            for e in range(g0.nElem):
+                f.write(f"{e + 1}\t" + "\t".join(str(x) for x in g0.conn[:, e]) + "\n")
+        with open(d / "d.dat", "w") as f:
+            for a, b, c in zip(dn, dd, dv):
+                f.write(f"{a}\t{b}\t{c:.8f}\n")
+        res = R.run_driver(driver, ["n.dat", "e.dat", "d.dat"], p, partition=(npid[g0.conn[0] - 1], npid) if p > 1 else None,
+                           cwd=str(d))
+        assert res.stopped is None, (seed, res.stopped)
+        mm = M.Mesh(np.round(coords, 8), g0.conn, dn.astype(np.int32), dd.astype(np.int32), dv.copy(), name="random")
+        num = D.number(mm, kind, p, npid if p > 1 else None)
+        fa = res.ranks[0].final_arrays
+        assert np.array_equal(num.NodeDofArrayNew.T, fa["nodedofarraynew"]) and np.array_equal(num.elemDof.T, fa["elemdofarray"]), seed
+        assert np.array_equal(num.solnApplied, fa["solnapplied"]), seed
+        rp, col = O.pattern(num.elemDof, num.size_global)
+        val, rhs, nbad = O.assemble(kind, num.conn_new, mm.coords, num.node_map_get_old, num.elemDof, num.solnApplied,
+                                    D.DEFAULT_ELEMDATA[kind], D.DEFAULT_TIMEDATA, rp, col)
+        grp, gcol, gval, grhs = res.system
+        assert nbad == 0 and np.array_equal(rp, grp) and np.array_equal(col, gcol), seed
+        if p == 1:
+            assert np.array_equal(val, gval) and np.array_equal(rhs, grhs), seed
+        else:
+            assert P.values_within(grp, val, gval, 1e-12) and P.vector_within(rhs, grhs, 1e-12), seed
+        assert np.abs(grhs).max() > 0
+
+
+@pytest.mark.skipif(not _reference_present(), reason="the reference tree exists only in the build container")
 def test_regenerated_vectors_equal_the_committed_files(tmp_path):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(GOLDEN, "make_reference_vectors.py"))
