@@ -19,7 +19,7 @@ import numpy as np
 from . import fortran_to_py as F
 from . import mocks
 from . import run_reference as R
-from .runtime import FortranExit, FortranStop, Ref, Runtime, _rt
+from .runtime import Runtime, _rt
 
 PFEM_POISSON_TRIA, PFEM_POISSON_TETRA, PFEM_ELASTICITY_TRIA, PFEM_ELASTICITY_TETRA = 0, 1, 2, 3
 

@@ -31,11 +31,6 @@ def _val(x):
     return x.v if isinstance(x, Ref) else x
 
 
-def _arr(x):
-    """a buffer argument: ndarray, or a Ref holding a scalar."""
-    return x
-
-
 class World:
     def __init__(self, size, partition=None):
         self.size = size

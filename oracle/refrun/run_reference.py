@@ -10,8 +10,6 @@ from __future__ import annotations
 import os
 import threading
 
-import numpy as np
-
 from . import fortran_to_py as F
 from . import mocks
 from .runtime import FortranExit, FortranStop, Runtime, _rt

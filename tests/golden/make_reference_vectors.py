@@ -32,7 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle.refrun import run_reference as R            # noqa: E402
-from oracle.refrun.runtime import FortranStop, Ref      # noqa: E402
+from oracle.refrun.runtime import FortranStop           # noqa: E402
 
 KIND_NAMES = ['poisson_tria', 'poisson_tetra', 'elasticity_tria', 'elasticity_tetra']
 KE = ['stiffnessresidualpoissonlineartria', 'stiffnessresidualpoissonlineartetra',

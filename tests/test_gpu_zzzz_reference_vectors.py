@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 
 from pfemfort_b200 import driver as D, explicit as X, mesh as M, solver as S
-from properties import values_within, vector_within
 
 pytestmark = pytest.mark.gpu
 

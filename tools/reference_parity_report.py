@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import pyoracle as O                                   # noqa: E402
-from pfemfort_b200 import driver as D, explicit as X, solver as S   # noqa: E402
+from pfemfort_b200 import driver as D, explicit as X               # noqa: E402
 import test_reference_vectors as T                                 # noqa: E402
 
 G = os.path.join(ROOT, "tests", "golden")
