@@ -272,3 +272,72 @@ def test_mock_mpi_collectives_on_three_ranks():
     [t.start() for t in ts]
     [t.join(30) for t in ts]
     assert out == [([10, 11, 12], 6, [0, 0])] * 3
+
+
+def test_free_form_interfaces_optional_arguments_and_c_binding(tmp_path):
+    """the free-form / ISO_C_BINDING side of the front end (what include/pfem_b200.f90 needs): `&` continuations, INTERFACE
+    blocks with BIND(C), VALUE vs by-address dummies, OPTIONAL + PRESENT, a by-address scalar result written back into a
+    local and into a derived-type component."""
+    import ctypes
+    import subprocess
+    from oracle.refrun.runtime import set_clib
+    csrc = tmp_path / "t.c"
+    csrc.write_text("""
+        int twice_plus(int a, double *x, int *out, const int *v, int n) {
+            int s = 0; for (int i = 0; i < n; i++) s += v[i];
+            *out = 2 * a + s; *x = *x + 0.5; return 7; }
+        int make_handle(void **h) { static int cell = 41; *h = &cell; return 0; }
+        int read_handle(void *h) { return *(int *)h + 1; }
+    """)
+    so = str(tmp_path / "libt.so")
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", so, str(csrc)], check=True)
+    text = """
+    ! free form: comments anywhere, & continuations
+    MODULE m
+      USE, INTRINSIC :: ISO_C_BINDING
+      IMPLICIT NONE
+      INTERFACE
+        INTEGER(C_INT) FUNCTION twice_plus(a, x, out, v, n) BIND(C)
+          IMPORT; INTEGER(C_INT), VALUE :: a, n
+          REAL(C_DOUBLE) :: x
+          INTEGER(C_INT) :: out, v(*)
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION make_handle(h) BIND(C)
+          IMPORT; TYPE(C_PTR) :: h
+        END FUNCTION
+        INTEGER(C_INT) FUNCTION read_handle(h) BIND(C)
+          IMPORT; TYPE(C_PTR), VALUE :: h
+        END FUNCTION
+      END INTERFACE
+      TYPE Box
+        TYPE(C_PTR) :: h = C_NULL_PTR
+        INTEGER :: n = 3
+      END TYPE Box
+    CONTAINS
+      SUBROUTINE drive(b, a, x, res, rc, opt)
+        CLASS(Box) :: b
+        INTEGER :: a, res, rc, &
+                   got            ! continued declaration
+        DOUBLE PRECISION :: x
+        INTEGER, OPTIONAL :: opt
+        INTEGER :: v(3)
+        v(1) = 1; v(2) = 2; v(3) = 3
+        rc = twice_plus(a, x, got, v, b%n)
+        res = got
+        IF (PRESENT(opt)) res = res + opt
+        rc = rc + make_handle(b%h)
+        res = res + 1000*read_handle(b%h)
+      END SUBROUTINE drive
+    END MODULE m
+    """
+    ns = {}
+    exec(compile(F.translate({"m.f90": text}), "<m.f90>", "exec"), ns)
+    set_clib(ctypes.CDLL(so))
+    b = ns["_new_box"]()
+    assert b.h is None and b.n == 3
+    x, res, rc = Ref(np.float64(1.25)), Ref(0), Ref(0)
+    ns["drive"](b, Ref(5), x, res, rc)
+    assert (x.v, rc.v) == (1.75, 7) and res.v == (2 * 5 + 6) + 1000 * 42 and b.h
+    res2 = Ref(0)
+    ns["drive"](b, Ref(5), Ref(np.float64(0.0)), res2, Ref(0), Ref(100))
+    assert res2.v == res.v + 100
