@@ -132,7 +132,7 @@ def make_elements(path, n=96):
 CASES = {
     # name: (driver, input prefix, kind, has ForceBC, swap local nodes 3 <-> 4, rank counts)
     'tria20x20': ('triapoissonparallelimpl1.F', 'tria20x20', 0, False, False, (1, 3)),
-    'tet10': ('tetrapoissonparallelimpl1.F', 'tet10', 1, False, False, (1, 2, 4)),
+    'tet10': ('tetrapoissonparallelimpl1.F', 'tet10', 1, False, False, (1, 2, 4, 8)),
     'cookmembranetria32': ('triaelasticityparallelimpl1.F', 'cookmembranetria32', 2, True, False, (1, 2)),
     'beam3Dtet6366': ('tetraelasticityparallelimpl1.F', 'beam3Dtet6366', 3, True, True, (1, 2)),
 }

@@ -23,7 +23,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KINDS = [S.POISSON_TRIA, S.POISSON_TETRA, S.ELASTICITY_TRIA, S.ELASTICITY_TETRA]
 CASES = {  # name: (kind, swap_34, rank counts)
     "tria20x20": (S.POISSON_TRIA, False, (1, 3)),
-    "tet10": (S.POISSON_TETRA, False, (1, 2, 4)),
+    "tet10": (S.POISSON_TETRA, False, (1, 2, 4, 8)),
     "cookmembranetria32": (S.ELASTICITY_TRIA, False, (1, 2)),
     "beam3Dtet6366": (S.ELASTICITY_TETRA, True, (1, 2)),
 }
